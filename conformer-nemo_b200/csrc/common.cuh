@@ -1,0 +1,88 @@
+// Shared declarations of the cfb CUDA library (internal; the public surface is include/cfb.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace cfb {
+
+using bf16 = __nv_bfloat16;
+
+// ---- epilogue selection shared by the tensor-core GEMM and the CUDA-core validation GEMM ---------------------
+enum EpiKind : int { EPI_LINEAR = 0, EPI_SWISH = 1, EPI_RELU = 2, EPI_RESID = 3, EPI_QKV = 4, EPI_GLU = 5 };
+
+struct EpiParams {
+  const float* bias = nullptr;   // per accumulator column (may be null)
+  const float* bias2 = nullptr;  // QKV: bias of the q+v copy
+  void* out = nullptr;           // TOut* (RESID: float*, read-modify-write)
+  long long ldo = 0;             // elements between output rows
+  float alpha = 1.f;             // RESID scale
+  const int32_t* lens = nullptr; // GLU / LINEAR: valid frames per sequence (null = no masking)
+  int frames_per_seq = 1;
+  int qkv_dp = 0;                // QKV: H * dk_pad
+  int M = 0;                     // valid output rows
+  int N = 0;                     // accumulator columns
+};
+
+// ---- launch descriptions ---------------------------------------------------------------------------------------
+struct GemmDesc {
+  // D (M x N) = A (M x K) * W^T (N x K); all row-major with the given leading dimensions (elements)
+  const void* A = nullptr;
+  long long lda = 0;
+  const void* W = nullptr;
+  long long ldw = 0;
+  int M = 0, N = 0, K = 0;
+  int epi = EPI_LINEAR;
+  bool out_bf16 = true;
+  EpiParams ep;
+};
+
+// implicit-GEMM view of the second strided 3x3 convolution of the subsampling stack:
+// input y1 in the parity-split channels-last layout [B][4 planes][Th][Fh][C] (plane = (t&1)*2 + (f&1)),
+// output y2 [B][To][Fo][C] with relu(bias + conv)
+struct ConvDesc {
+  const void* y_in = nullptr;
+  const void* W = nullptr;  // [C_out][9*C_in], k = (kh*3+kw)*C_in + c
+  const float* bias = nullptr;
+  void* y_out = nullptr;
+  int B = 0, C_in = 0, C_out = 0;
+  int Th = 0, Fh = 0;  // plane extents of the input
+  int To = 0, Fo = 0;  // output extents
+};
+
+struct AttnDesc {
+  const void* qkv = nullptr;  // (B*T, 4*Dp)
+  const void* pos = nullptr;  // (2T-1, ld_pos), this layer's columns start at pos
+  long long ld_pos = 0;
+  void* ctx = nullptr;  // (B*T, Dp)
+  const int32_t* lens = nullptr;
+  int B = 0, T = 0, H = 0, dk = 0, dkp = 0;
+};
+
+// ---- launchers (each returns a cudaError_t-compatible int; 0 = success) ------------------------------------------
+int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err);
+int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err);
+int launch_gemm_simt(const GemmDesc& g, float* scratch, cudaStream_t st, std::string* err);
+int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err);
+int launch_attn_simt(const AttnDesc& a, cudaStream_t st, std::string* err);
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int rows, int d,
+                     const int32_t* lens, int frames_per_seq, cudaStream_t st);
+int launch_depthwise(const void* x, const float* taps, const float* bias, void* out, bool is_bf16, int B, int T, int d,
+                     int ksize, cudaStream_t st);
+int launch_lengths(const long long* lengths, int32_t* out, int B, int T_full, int n_stages, cudaStream_t st);
+int launch_pos_table(void* out, bool out_bf16, const float* div_term, int T, int d, cudaStream_t st);
+// first strided conv (1 -> C channels) + ReLU from (B, F, T) features into the parity-split channels-last layout
+int launch_subsample_first(const void* feats, bool feats_bf16, const float* w9, const float* bias, void* y_out,
+                           bool out_bf16, int B, int F, int T, int C, int T1, int F1, int Th, int Fh, cudaStream_t st);
+// validation path: gather the 3x3/s2 patches of a parity-split tensor into a dense (rows x 9*C) fp32 matrix
+int launch_im2col(const float* y_in, float* cols, int B, int C, int Th, int Fh, int To, int Fo, cudaStream_t st);
+
+// TMA descriptor encoder (cuTensorMapEncodeTiled resolved through the runtime; libcuda is not linked)
+bool encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, std::string* err);
+
+}  // namespace cfb

@@ -1,0 +1,369 @@
+// Memory-bound kernels of the encoder: LayerNorm, depth-wise time convolution (+ folded BatchNorm + Swish),
+// the first 1->C strided convolution of the subsampling stack, the relative positional table, calc_length, and the
+// validation path's im2col.  All are coalesced along the channel dimension with 128-bit accesses; reductions use
+// warp shuffles; the depth-wise kernel stages its time halo in shared memory.
+#include "common.cuh"
+
+namespace cfb {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store4(bf16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row; the row lives in registers (d <= 32*4*kMaxVec) between the two reduction passes, so x is read
+// from HBM exactly once.  Statistics in fp32: mean, then the centred second moment (matches F.layer_norm).
+constexpr int kMaxVec = 8;  // float4 per lane -> d <= 1024
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, TOut* __restrict__ out,
+                                                        int rows, int d, const int32_t* __restrict__ lens,
+                                                        int frames_per_seq) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = d >> 2;  // float4 per row
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * d);
+  TOut* orow = out + static_cast<long long>(row) * d;
+  if (lens != nullptr) {
+    const int seq = row / frames_per_seq;
+    if (row - seq * frames_per_seq >= lens[seq]) {
+      for (int i = lane; i < nvec; i += 32) store4(orow + 4 * i, 0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+  }
+  float4 v[kMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nvec) {
+      v[k] = xr[i];
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(d);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nvec) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, e = v[k].w - mean;
+      q += (a * a + b * b) + (c * c + e * e);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(d) + 1e-5f);
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i);
+      store4(orow + 4 * i, (v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y,
+             (v[k].z - mean) * rstd * g.z + b.z, (v[k].w - mean) * rstd * g.w + b.w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ depth-wise conv
+// out[b,t,c] = swish(bias[c] + sum_k taps[c][k] * x[b, t + k - (K-1)/2, c]), zero outside [0,T).
+// Block: 64 channels x 64 frames of one sequence; the (64 + K - 1)-frame halo tile is staged in shared memory as
+// fp32; each thread owns a channel pair and 8 consecutive frames and slides the K-tap window over registers.
+constexpr int kDwC = 64, kDwT = 64, kDwMaxK = 31;
+
+template <typename T>
+__device__ __forceinline__ float2 load2(const T* p);
+template <>
+__device__ __forceinline__ float2 load2<float>(const float* p) {
+  return *reinterpret_cast<const float2*>(p);
+}
+template <>
+__device__ __forceinline__ float2 load2<bf16>(const bf16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+__device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store2(bf16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+template <typename T, bool kFast>
+__global__ void __launch_bounds__(256) depthwise_kernel(const T* __restrict__ x, const float* __restrict__ taps,
+                                                        const float* __restrict__ bias, T* __restrict__ out, int T_len,
+                                                        int d, int ksize) {
+  __shared__ __align__(16) float tile[kDwT + kDwMaxK - 1][kDwC + 2];
+  const int half = (ksize - 1) / 2;
+  const int tblocks = (T_len + kDwT - 1) / kDwT;
+  const int b = blockIdx.x / tblocks;
+  const int t0 = (blockIdx.x % tblocks) * kDwT;
+  const int c0 = blockIdx.y * kDwC;
+  const T* xb = x + static_cast<long long>(b) * T_len * d;
+  T* ob = out + static_cast<long long>(b) * T_len * d;
+  const int span = kDwT + ksize - 1;
+  // stage: 32 channel pairs x span frames
+  for (int i = threadIdx.x; i < span * (kDwC / 2); i += 256) {
+    const int r = i / (kDwC / 2), cp = i % (kDwC / 2);
+    const int t = t0 - half + r, c = c0 + 2 * cp;
+    float2 v = make_float2(0.f, 0.f);
+    if (t >= 0 && t < T_len && c < d) v = load2<T>(xb + static_cast<long long>(t) * d + c);
+    tile[r][2 * cp] = v.x;
+    tile[r][2 * cp + 1] = v.y;
+  }
+  __syncthreads();
+  const int cp = threadIdx.x & 31;  // channel pair
+  const int strip = threadIdx.x >> 5;  // 8 strips of 8 frames
+  const int c = c0 + 2 * cp;
+  if (c >= d) return;
+  float w0[kDwMaxK], w1[kDwMaxK];
+#pragma unroll
+  for (int k = 0; k < kDwMaxK; ++k) {
+    w0[k] = (k < ksize) ? __ldg(taps + static_cast<long long>(c) * ksize + k) : 0.f;
+    w1[k] = (k < ksize) ? __ldg(taps + static_cast<long long>(c + 1) * ksize + k) : 0.f;
+  }
+  float a0[8], a1[8];
+  const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
+#pragma unroll
+  for (int o = 0; o < 8; ++o) a0[o] = b0, a1[o] = b1;
+#pragma unroll
+  for (int j = 0; j < 8 + kDwMaxK - 1; ++j) {
+    if (j < 8 + ksize - 1) {
+      const float2 vv = *reinterpret_cast<const float2*>(&tile[strip * 8 + j][2 * cp]);
+      const float v0 = vv.x, v1 = vv.y;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const int k = j - o;
+        if (k >= 0 && k < kDwMaxK) {
+          a0[o] = fmaf(w0[k], v0, a0[o]);
+          a1[o] = fmaf(w1[k], v1, a1[o]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const int t = t0 + strip * 8 + o;
+    if (t < T_len) {
+      float s0, s1;
+      if constexpr (kFast) {
+        s0 = __fdividef(a0[o], 1.f + __expf(-a0[o]));
+        s1 = __fdividef(a1[o], 1.f + __expf(-a1[o]));
+      } else {
+        s0 = a0[o] / (1.f + expf(-a0[o]));
+        s1 = a1[o] / (1.f + expf(-a1[o]));
+      }
+      store2(ob + static_cast<long long>(t) * d + c, s0, s1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ calc_length
+// subsampling.py:272-282 evaluates floor((float(L) + 2p - k) / s + 1) in float32 per stage and truncates to int32;
+// the same IEEE operations are issued here (no contraction) so the result is bit-identical for every int64 input.
+__global__ void lengths_kernel(const long long* __restrict__ lengths, int32_t* __restrict__ out, int B, int T_full,
+                               int n_stages) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  if (lengths == nullptr) {
+    float f = static_cast<float>(T_full);  // length=None: every row is T_full long (conformer_encoder.py:243-246)
+    for (int s = 0; s < n_stages; ++s) f = floorf(__fadd_rn(__fdiv_rn(__fadd_rn(f, -1.0f), 2.0f), 1.0f));
+    out[i] = static_cast<int32_t>(f);
+    return;
+  }
+  float f = __ll2float_rn(lengths[i]);
+  for (int s = 0; s < n_stages; ++s) f = floorf(__fadd_rn(__fdiv_rn(__fadd_rn(f, -1.0f), 2.0f), 1.0f));
+  out[i] = static_cast<int32_t>(f);
+}
+
+// ------------------------------------------------------------------------------------------------ positional table
+// row k <-> relative position (T-1-k); even columns sin(pos * div[m]), odd columns cos(pos * div[m])
+// (multi_head_attention.py:235-248,292).  Accurate sinf/cosf: the argument reaches several thousand radians.
+template <typename TOut>
+__global__ void pos_table_kernel(TOut* __restrict__ out, const float* __restrict__ div_term, int T, int d) {
+  const int k = blockIdx.x;
+  const float pos = static_cast<float>(T - 1 - k);
+  for (int m = threadIdx.x; m < d / 2; m += blockDim.x) {
+    const float ang = __fmul_rn(pos, div_term[m]);
+    store2(out + static_cast<long long>(k) * d + 2 * m, sinf(ang), cosf(ang));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ first strided conv
+// y1[b, t1, f1, c] = relu(bias[c] + sum_{kh,kw} w[c][kh][kw] * x[b][2 f1 + kw - 1][2 t1 + kh - 1])   (x is (B,F,T))
+// written in the parity-split channels-last layout [B][plane = (t1&1)*2 + (f1&1)][Th][Fh][C] that lets the second
+// convolution fetch each filter tap as one dense TMA box.  Positions with t1 >= T1 or f1 >= F1 are written as 0.
+constexpr int kS1T = 16;  // t1 rows per block
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) subsample_first_kernel(const TIn* __restrict__ feats,
+                                                              const float* __restrict__ w9,
+                                                              const float* __restrict__ bias, TOut* __restrict__ y,
+                                                              int F, int T, int C, int T1, int F1, int Th, int Fh) {
+  extern __shared__ float patch[];  // [F + 2][2*kS1T + 1 (+1 pad)]  frames 2*t1_0 - 1 .. 2*(t1_0 + kS1T - 1) + 1
+  const int pw = 2 * kS1T + 2;
+  const int tblocks = (2 * Th + kS1T - 1) / kS1T;
+  const int b = blockIdx.x / tblocks;
+  const int t1_0 = (blockIdx.x % tblocks) * kS1T;
+  const TIn* xb = feats + static_cast<long long>(b) * F * T;
+  for (int i = threadIdx.x; i < (F + 2) * (2 * kS1T + 1); i += 256) {
+    const int fr = i / (2 * kS1T + 1), tc = i % (2 * kS1T + 1);
+    const int f = fr - 1, t = 2 * t1_0 - 1 + tc;
+    float v = 0.f;
+    if (f >= 0 && f < F && t >= 0 && t < T) v = static_cast<float>(xb[static_cast<long long>(f) * T + t]);
+    patch[fr * pw + tc] = v;
+  }
+  __syncthreads();
+  const int groups = C / 8;  // 8 channels per thread
+  const int positions = kS1T * 2 * Fh;
+  for (int item = threadIdx.x; item < positions * groups; item += 256) {
+    const int g = item % groups;
+    const int pos = item / groups;
+    const int f1 = pos % (2 * Fh);
+    const int tt = pos / (2 * Fh);
+    const int t1 = t1_0 + tt;
+    if (t1 >= 2 * Th) continue;
+    float acc[8];
+    const bool live = (t1 < T1) && (f1 < F1);
+    if (live) {
+      float in[9];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = patch[(2 * f1 + kw) * pw + (2 * tt + kh)];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        float a = __ldg(bias + c);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) a = fmaf(__ldg(w9 + c * 9 + q), in[q], a);
+        acc[j] = fmaxf(a, 0.f);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    }
+    const int plane = (t1 & 1) * 2 + (f1 & 1);
+    const long long off =
+        ((((static_cast<long long>(b) * 4 + plane) * Th + (t1 >> 1)) * Fh + (f1 >> 1)) * C) + g * 8;
+    store4(y + off, acc[0], acc[1], acc[2], acc[3]);
+    store4(y + off + 4, acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ im2col (validation)
+__global__ void im2col_kernel(const float* __restrict__ y, float* __restrict__ cols, int B, int C, int Th, int Fh,
+                              int To, int Fo) {
+  const long long total = static_cast<long long>(B) * To * Fo * 9 * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    long long r = i / C;
+    const int tap = static_cast<int>(r % 9);
+    r /= 9;
+    const int fo = static_cast<int>(r % Fo);
+    r /= Fo;
+    const int to = static_cast<int>(r % To);
+    const int b = static_cast<int>(r / To);
+    const int kh = tap / 3, kw = tap % 3;
+    const int t1 = 2 * to + kh - 1, f1 = 2 * fo + kw - 1;
+    float v = 0.f;
+    if (t1 >= 0 && t1 < 2 * Th && f1 >= 0 && f1 < 2 * Fh) {
+      const int plane = (t1 & 1) * 2 + (f1 & 1);
+      v = y[((((static_cast<long long>(b) * 4 + plane) * Th + (t1 >> 1)) * Fh + (f1 >> 1)) * C) + c];
+    }
+    cols[i] = v;
+  }
+}
+
+}  // namespace
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int rows, int d,
+                     const int32_t* lens, int frames_per_seq, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (d % 4 != 0 || d > 128 * kMaxVec) return -1;
+  const int blocks = (rows + 7) / 8;
+  if (out_bf16)
+    layernorm_kernel<bf16><<<blocks, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<bf16*>(out), rows, d, lens,
+                                                   frames_per_seq);
+  else
+    layernorm_kernel<float><<<blocks, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<float*>(out), rows, d, lens,
+                                                    frames_per_seq);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_depthwise(const void* x, const float* taps, const float* bias, void* out, bool is_bf16, int B, int T, int d,
+                     int ksize, cudaStream_t st) {
+  if (B <= 0 || T <= 0) return 0;
+  if (ksize > kDwMaxK || (ksize & 1) == 0 || d % 2 != 0) return -1;
+  dim3 grid(B * ((T + kDwT - 1) / kDwT), (d + kDwC - 1) / kDwC);
+  if (is_bf16)
+    depthwise_kernel<bf16, true><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), taps, bias,
+                                                       reinterpret_cast<bf16*>(out), T, d, ksize);
+  else
+    depthwise_kernel<float, false><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), taps, bias,
+                                                         reinterpret_cast<float*>(out), T, d, ksize);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_lengths(const long long* lengths, int32_t* out, int B, int T_full, int n_stages, cudaStream_t st) {
+  if (B <= 0) return 0;
+  lengths_kernel<<<(B + 127) / 128, 128, 0, st>>>(lengths, out, B, T_full, n_stages);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_pos_table(void* out, bool out_bf16, const float* div_term, int T, int d, cudaStream_t st) {
+  if (T <= 0) return 0;
+  if (out_bf16)
+    pos_table_kernel<bf16><<<2 * T - 1, 128, 0, st>>>(reinterpret_cast<bf16*>(out), div_term, T, d);
+  else
+    pos_table_kernel<float><<<2 * T - 1, 128, 0, st>>>(reinterpret_cast<float*>(out), div_term, T, d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_subsample_first(const void* feats, bool feats_bf16, const float* w9, const float* bias, void* y_out,
+                           bool out_bf16, int B, int F, int T, int C, int T1, int F1, int Th, int Fh, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (C % 8 != 0) return -1;
+  const int tblocks = (2 * Th + kS1T - 1) / kS1T;
+  const size_t smem = static_cast<size_t>(F + 2) * (2 * kS1T + 2) * sizeof(float);
+  const int grid = B * tblocks;
+#define CFB_S1(TIN, TOUT)                                                                                         \
+  subsample_first_kernel<TIN, TOUT><<<grid, 256, smem, st>>>(reinterpret_cast<const TIN*>(feats), w9, bias,       \
+                                                             reinterpret_cast<TOUT*>(y_out), F, T, C, T1, F1, Th, Fh)
+  if (feats_bf16) {
+    if (out_bf16)
+      CFB_S1(bf16, bf16);
+    else
+      CFB_S1(bf16, float);
+  } else {
+    if (out_bf16)
+      CFB_S1(float, bf16);
+    else
+      CFB_S1(float, float);
+  }
+#undef CFB_S1
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_im2col(const float* y_in, float* cols, int B, int C, int Th, int Fh, int To, int Fo, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * To * Fo * 9 * C;
+  if (total <= 0) return 0;
+  const int blocks = static_cast<int>(total / 256 + 1 < 65535 * 8 ? total / 256 + 1 : 65535 * 8);
+  im2col_kernel<<<blocks, 256, 0, st>>>(y_in, cols, B, C, Th, Fh, To, Fo);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace cfb

@@ -1,0 +1,810 @@
+// Host side of the cfb library: handle, weight ingestion + packing, workspace planning, the forward schedule and the
+// C ABI of include/cfb.h.  The forward pass is enqueue-only: no allocation, no synchronisation, one stream.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "../../include/cfb.h"
+#include "common.cuh"
+
+using namespace cfb;
+
+namespace {
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// device arena entry: offset in bytes
+struct Slot {
+  size_t off = 0;
+};
+
+struct LayerW {
+  // LayerNorm affine (fp32): ff1, att, conv, ff2, out
+  Slot ln_g[5], ln_b[5];
+  Slot ff_w1[2], ff_b1[2], ff_w2[2], ff_b2[2];
+  Slot w_qkv, b_qkv, b_qv, w_out, b_out;
+  Slot w_pw1, b_pw1, dw_taps, dw_bias, w_pw2, b_pw2;
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct cfb_handle {
+  cfb_config cfg;
+  int device = 0;
+  bool validate = false;  // CFB_PREC_FP32_VALIDATE
+  // derived
+  int d = 0, C = 0, F0 = 0, F1 = 0, F2 = 0, Fh = 0, dff = 0, H = 0, dk = 0, dkp = 64, Dp = 0, L = 0, ksize = 0;
+  int d_out = 0;
+  bool has_out_proj = false;
+  std::map<std::string, HostTensor> staged;
+  bool finalized = false;
+  // device arena
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  Slot sub_w1, sub_b1, sub_w2, sub_b2, sub_w3, sub_b3, w_pos, div_term, w_oproj, b_oproj;
+  std::vector<LayerW> layers;
+  int launches = 0;
+  mutable std::string err;
+
+  size_t esz() const { return validate ? 4 : 2; }  // bytes per activation / matrix element
+  template <typename T>
+  T* at(const Slot& s) const {
+    return reinterpret_cast<T*>(arena + s.off);
+  }
+};
+
+namespace {
+
+int fail(const cfb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+int conv_out(int n) { return (n - 1) / 2 + 1; }  // k=3, s=2, p=1 (n >= 1)
+
+struct Plan {
+  int B, T, T1, T2, Th, N, P;  // P = 2*T2-1
+  size_t y1, y2, x, a, hbuf, qkv, ctx, g, c, pe, pos, raw, cols, total;
+};
+
+Plan make_plan(const cfb_handle* h, int B, int T) {
+  Plan p{};
+  p.B = B;
+  p.T = T;
+  p.T1 = conv_out(T);
+  p.T2 = conv_out(p.T1);
+  p.Th = (p.T1 + 1) / 2;
+  p.N = B * p.T2;
+  p.P = 2 * p.T2 - 1;
+  const size_t e = h->esz();
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes);
+    return o;
+  };
+  const size_t N = static_cast<size_t>(p.N);
+  p.y1 = take(static_cast<size_t>(B) * 4 * p.Th * h->Fh * h->C * e);
+  p.y2 = take(N * h->F2 * h->C * e);
+  p.x = take(N * h->d * 4);
+  p.a = take(N * h->d * e);
+  p.hbuf = take(N * h->dff * e);
+  p.qkv = take(N * 4 * h->Dp * e);
+  p.ctx = take(N * h->Dp * e);
+  p.g = take(N * h->d * e);
+  p.c = take(N * h->d * e);
+  p.pe = take(static_cast<size_t>(p.P) * h->d * e);
+  p.pos = take(static_cast<size_t>(p.P) * h->L * h->Dp * e);
+  if (h->validate) {
+    size_t raw = N * h->dff;
+    raw = std::max(raw, N * 3 * h->Dp);
+    raw = std::max(raw, static_cast<size_t>(p.P) * h->L * h->Dp);
+    raw = std::max(raw, N * h->F2 * h->C);
+    raw = std::max(raw, N * 2 * h->d);
+    raw = std::max(raw, N * static_cast<size_t>(std::max(h->d_out, h->d)));
+    p.raw = take(raw * 4);
+    p.cols = take(N * h->F2 * 9 * h->C * 4);
+  }
+  p.total = off;
+  return p;
+}
+
+const HostTensor* find(const cfb_handle* h, const std::string& key) {
+  auto it = h->staged.find(key);
+  return it == h->staged.end() ? nullptr : &it->second;
+}
+
+bool shape_is(const HostTensor* t, std::initializer_list<int64_t> want) {
+  if (!t || t->shape.size() != want.size()) return false;
+  size_t i = 0;
+  for (auto w : want)
+    if (t->shape[i++] != w) return false;
+  return true;
+}
+
+// arena builder: host-side image + slots
+struct ArenaBuilder {
+  std::vector<uint8_t> img;
+  Slot put_f32(const std::vector<float>& v) {
+    Slot s;
+    s.off = align_up(img.size());
+    img.resize(s.off + v.size() * 4);
+    memcpy(img.data() + s.off, v.data(), v.size() * 4);
+    return s;
+  }
+  Slot put_mat(const std::vector<float>& v, bool as_f32) {
+    if (as_f32) return put_f32(v);
+    Slot s;
+    s.off = align_up(img.size());
+    img.resize(s.off + v.size() * 2);
+    bf16* dst = reinterpret_cast<bf16*>(img.data() + s.off);
+    for (size_t i = 0; i < v.size(); ++i) dst[i] = __float2bfloat16_rn(v[i]);
+    return s;
+  }
+};
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+const char* cfb_last_error(const cfb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cfb_create(const cfb_config* cfg, int device, cfb_handle** out) {
+  if (!cfg || !out) {
+    g_create_error = "cfb_create: null argument";
+    return CFB_ERR_INVALID_ARG;
+  }
+  *out = nullptr;
+  auto bad = [&](int code, const std::string& m) {
+    g_create_error = "cfb_create: " + m;
+    return code;
+  };
+  if (cfg->feat_in < 1 || cfg->n_layers < 1 || cfg->d_model < 16 || cfg->n_heads < 1 || cfg->ff_expansion_factor < 1)
+    return bad(CFB_ERR_INVALID_ARG, "feat_in, n_layers, d_model, n_heads and ff_expansion_factor must be positive");
+  if (cfg->d_model % cfg->n_heads) return bad(CFB_ERR_INVALID_ARG, "d_model must be divisible by n_heads");
+  if (cfg->subsampling_factor != 4)
+    return bad(CFB_ERR_UNSUPPORTED, "only subsampling_factor=4 (two strided convolutions) is supported");
+  if (cfg->d_model % 16) return bad(CFB_ERR_UNSUPPORTED, "d_model must be a multiple of 16");
+  if (cfg->d_model > 1024) return bad(CFB_ERR_UNSUPPORTED, "d_model > 1024 is not supported");
+  if (cfg->d_model / cfg->n_heads > 64) return bad(CFB_ERR_UNSUPPORTED, "head dimension > 64 is not supported");
+  if ((cfg->d_model / cfg->n_heads) % 2) return bad(CFB_ERR_UNSUPPORTED, "head dimension must be even");
+  if (cfg->conv_kernel_size < 1 || cfg->conv_kernel_size > 31 || cfg->conv_kernel_size % 2 == 0)
+    return bad(CFB_ERR_UNSUPPORTED, "conv_kernel_size must be odd and <= 31");
+  const int C = cfg->subsampling_conv_channels == -1 ? cfg->d_model : cfg->subsampling_conv_channels;
+  if (C < 8 || C % 8) return bad(CFB_ERR_UNSUPPORTED, "subsampling_conv_channels must be a multiple of 8");
+  if (cfg->precision != CFB_PREC_BF16 && cfg->precision != CFB_PREC_FP32_VALIDATE)
+    return bad(CFB_ERR_INVALID_ARG, "unknown precision");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return bad(CFB_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) return bad(CFB_ERR_UNSUPPORTED, "the kernels are built for sm_100a (Blackwell B200) only");
+
+  cfb_handle* h = new cfb_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->validate = cfg->precision == CFB_PREC_FP32_VALIDATE;
+  h->d = cfg->d_model;
+  h->C = C;
+  h->F0 = cfg->feat_in;
+  h->F1 = conv_out(h->F0);
+  h->F2 = conv_out(h->F1);
+  h->Fh = (h->F1 + 1) / 2;
+  h->dff = cfg->d_model * cfg->ff_expansion_factor;
+  h->H = cfg->n_heads;
+  h->dk = h->d / h->H;
+  h->dkp = 64;
+  h->Dp = h->H * h->dkp;
+  h->L = cfg->n_layers;
+  h->ksize = cfg->conv_kernel_size;
+  h->has_out_proj = cfg->feat_out > 0 && cfg->feat_out != cfg->d_model;
+  h->d_out = h->has_out_proj ? cfg->feat_out : h->d;
+  if (h->dff % 8 || h->d_out % 8) {
+    delete h;
+    return bad(CFB_ERR_UNSUPPORTED, "d_ff and feat_out must be multiples of 8");
+  }
+  *out = h;
+  return CFB_OK;
+}
+
+void cfb_destroy(cfb_handle* h) {
+  if (!h) return;
+  if (h->arena) {
+    cudaSetDevice(h->device);
+    cudaFree(h->arena);
+  }
+  delete h;
+}
+
+int cfb_set_weight(cfb_handle* h, const char* ref_key, const void* ptr, int dtype, const int64_t* shape, int ndim) {
+  if (!h) return CFB_ERR_INVALID_ARG;
+  if (!ref_key || !ptr || ndim < 0 || ndim > 8 || (ndim > 0 && !shape))
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_set_weight: null argument");
+  const std::string key(ref_key);
+  const std::string tail = "num_batches_tracked";
+  if (key.size() >= tail.size() && key.compare(key.size() - tail.size(), tail.size(), tail) == 0) return CFB_OK;
+  HostTensor t;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] < 0) return fail(h, CFB_ERR_INVALID_ARG, "cfb_set_weight: negative dimension for " + key);
+    t.shape.push_back(shape[i]);
+    n *= shape[i];
+  }
+  t.data.resize(static_cast<size_t>(n));
+  cudaSetDevice(h->device);
+  cudaError_t e = cudaSuccess;
+  if (dtype == CFB_F32) {
+    e = cudaMemcpy(t.data.data(), ptr, static_cast<size_t>(n) * 4, cudaMemcpyDefault);
+  } else if (dtype == CFB_BF16 || dtype == CFB_F16) {
+    std::vector<uint16_t> tmp(static_cast<size_t>(n));
+    e = cudaMemcpy(tmp.data(), ptr, static_cast<size_t>(n) * 2, cudaMemcpyDefault);
+    if (e == cudaSuccess) {
+      for (int64_t i = 0; i < n; ++i) {
+        if (dtype == CFB_BF16) {
+          uint32_t u = static_cast<uint32_t>(tmp[i]) << 16;
+          memcpy(&t.data[i], &u, 4);
+        } else {
+          __half hv;
+          memcpy(&hv, &tmp[i], 2);
+          t.data[i] = __half2float(hv);
+        }
+      }
+    }
+  } else {
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_set_weight: dtype must be f32, bf16 or f16 for " + key);
+  }
+  if (e != cudaSuccess) return fail(h, CFB_ERR_CUDA, std::string("cfb_set_weight: copy failed: ") + cudaGetErrorString(e));
+  h->staged[key] = std::move(t);
+  h->finalized = false;
+  return CFB_OK;
+}
+
+int cfb_finalize_weights(cfb_handle* h) {
+  if (!h) return CFB_ERR_INVALID_ARG;
+  const int d = h->d, C = h->C, F2 = h->F2, dff = h->dff, H = h->H, dk = h->dk, dkp = h->dkp, Dp = h->Dp, L = h->L;
+  const int ks = h->ksize;
+  const bool f32 = h->validate;
+  std::string missing;
+  auto need = [&](const std::string& key, std::initializer_list<int64_t> shape) -> const HostTensor* {
+    const HostTensor* t = find(h, key);
+    if (!t) {
+      if (missing.empty()) missing = "missing weight: " + key;
+      return nullptr;
+    }
+    if (!shape_is(t, shape)) {
+      if (missing.empty()) {
+        missing = "bad shape for " + key + ": got (";
+        for (auto s : t->shape) missing += std::to_string(s) + ",";
+        missing += ") expected (";
+        for (auto s : shape) missing += std::to_string(s) + ",";
+        missing += ")";
+      }
+      return nullptr;
+    }
+    return t;
+  };
+
+  ArenaBuilder ab;
+  // ---- subsampling (subsampling.py:99-116,160)
+  const HostTensor* c0w = need("pre_encode.conv.0.weight", {C, 1, 3, 3});
+  const HostTensor* c0b = need("pre_encode.conv.0.bias", {C});
+  const HostTensor* c2w = need("pre_encode.conv.2.weight", {C, C, 3, 3});
+  const HostTensor* c2b = need("pre_encode.conv.2.bias", {C});
+  const HostTensor* ow = need("pre_encode.out.weight", {d, static_cast<int64_t>(C) * F2});
+  const HostTensor* ob = need("pre_encode.out.bias", {d});
+  if (!missing.empty()) return fail(h, CFB_ERR_MISSING_WEIGHT, "cfb_finalize_weights: " + missing);
+  h->sub_w1 = ab.put_f32(c0w->data);
+  h->sub_b1 = ab.put_f32(c0b->data);
+  {
+    std::vector<float> w(static_cast<size_t>(C) * 9 * C);
+    for (int n = 0; n < C; ++n)
+      for (int c = 0; c < C; ++c)
+        for (int t = 0; t < 9; ++t)
+          w[(static_cast<size_t>(n) * 9 + t) * C + c] = c2w->data[(static_cast<size_t>(n) * C + c) * 9 + t];
+    h->sub_w2 = ab.put_mat(w, f32);
+    h->sub_b2 = ab.put_f32(c2b->data);
+  }
+  {
+    // fold x * sqrt(d_model) (multi_head_attention.py:305-306) and permute K from (c, f) to (f, c)
+    const float xs = h->cfg.xscaling ? sqrtf(static_cast<float>(d)) : 1.f;
+    std::vector<float> w(static_cast<size_t>(d) * F2 * C), b(d);
+    for (int n = 0; n < d; ++n) {
+      for (int c = 0; c < C; ++c)
+        for (int f = 0; f < F2; ++f)
+          w[(static_cast<size_t>(n) * F2 + f) * C + c] = ow->data[static_cast<size_t>(n) * C * F2 + c * F2 + f] * xs;
+      b[n] = ob->data[n] * xs;
+    }
+    h->sub_w3 = ab.put_mat(w, f32);
+    h->sub_b3 = ab.put_f32(b);
+  }
+  // ---- sinusoid frequencies (multi_head_attention.py:238-241)
+  {
+    std::vector<float> div(d / 2);
+    const HostTensor* dt = find(h, "pos_enc.div_term");
+    if (dt && dt->numel() == d / 2) {
+      div = dt->data;
+    } else {
+      const float cst = static_cast<float>(-(log(10000.0) / d));
+      for (int m = 0; m < d / 2; ++m) div[m] = expf(static_cast<float>(2 * m) * cst);
+    }
+    h->div_term = ab.put_f32(div);
+  }
+  // ---- layers
+  h->layers.assign(L, LayerW());
+  std::vector<float> wpos(static_cast<size_t>(L) * Dp * d, 0.f);
+  static const char* ln_names[5] = {"norm_feed_forward1", "norm_self_att", "norm_conv", "norm_feed_forward2", "norm_out"};
+  for (int l = 0; l < L && missing.empty(); ++l) {
+    const std::string p = "layers." + std::to_string(l) + ".";
+    LayerW& lw = h->layers[l];
+    for (int i = 0; i < 5; ++i) {
+      const HostTensor* g = need(p + ln_names[i] + ".weight", {d});
+      const HostTensor* b = need(p + ln_names[i] + ".bias", {d});
+      if (!g || !b) break;
+      lw.ln_g[i] = ab.put_f32(g->data);
+      lw.ln_b[i] = ab.put_f32(b->data);
+    }
+    for (int f = 0; f < 2 && missing.empty(); ++f) {
+      const std::string q = p + (f == 0 ? "feed_forward1." : "feed_forward2.");
+      const HostTensor* w1 = need(q + "linear1.weight", {dff, d});
+      const HostTensor* b1 = need(q + "linear1.bias", {dff});
+      const HostTensor* w2 = need(q + "linear2.weight", {d, dff});
+      const HostTensor* b2 = need(q + "linear2.bias", {d});
+      if (!w1 || !b1 || !w2 || !b2) break;
+      lw.ff_w1[f] = ab.put_mat(w1->data, f32);
+      lw.ff_b1[f] = ab.put_f32(b1->data);
+      lw.ff_w2[f] = ab.put_mat(w2->data, f32);
+      lw.ff_b2[f] = ab.put_f32(b2->data);
+    }
+    if (!missing.empty()) break;
+    const std::string a = p + "self_attn.";
+    const HostTensor* wq = need(a + "linear_q.weight", {d, d});
+    const HostTensor* wk = need(a + "linear_k.weight", {d, d});
+    const HostTensor* wv = need(a + "linear_v.weight", {d, d});
+    const HostTensor* bq = need(a + "linear_q.bias", {d});
+    const HostTensor* bk = need(a + "linear_k.bias", {d});
+    const HostTensor* bv = need(a + "linear_v.bias", {d});
+    const HostTensor* wo = need(a + "linear_out.weight", {d, d});
+    const HostTensor* bo = need(a + "linear_out.bias", {d});
+    const HostTensor* wp = need(a + "linear_pos.weight", {d, d});
+    const HostTensor* pu = need(a + "pos_bias_u", {H, dk});
+    const HostTensor* pv = need(a + "pos_bias_v", {H, dk});
+    if (!missing.empty()) break;
+    {
+      // fused projection: accumulator columns [q | k | v], each head padded from dk to dkp columns with zero rows;
+      // bias = [bq + u | bk | bv], bias2 = bq + v  (multi_head_attention.py:190-193)
+      std::vector<float> w(static_cast<size_t>(3) * Dp * d, 0.f), b(3 * Dp, 0.f), b2(Dp, 0.f);
+      std::vector<float> wo_p(static_cast<size_t>(d) * Dp, 0.f);
+      for (int hh = 0; hh < H; ++hh)
+        for (int c = 0; c < dk; ++c) {
+          const int src = hh * dk + c, dst = hh * dkp + c;
+          memcpy(&w[static_cast<size_t>(dst) * d], &wq->data[static_cast<size_t>(src) * d], d * 4);
+          memcpy(&w[static_cast<size_t>(Dp + dst) * d], &wk->data[static_cast<size_t>(src) * d], d * 4);
+          memcpy(&w[static_cast<size_t>(2 * Dp + dst) * d], &wv->data[static_cast<size_t>(src) * d], d * 4);
+          b[dst] = bq->data[src] + pu->data[src];
+          b2[dst] = bq->data[src] + pv->data[src];
+          b[Dp + dst] = bk->data[src];
+          b[2 * Dp + dst] = bv->data[src];
+          memcpy(&wpos[(static_cast<size_t>(l) * Dp + dst) * d], &wp->data[static_cast<size_t>(src) * d], d * 4);
+          for (int n = 0; n < d; ++n) wo_p[static_cast<size_t>(n) * Dp + dst] = wo->data[static_cast<size_t>(n) * d + src];
+        }
+      lw.w_qkv = ab.put_mat(w, f32);
+      lw.b_qkv = ab.put_f32(b);
+      lw.b_qv = ab.put_f32(b2);
+      lw.w_out = ab.put_mat(wo_p, f32);
+      lw.b_out = ab.put_f32(bo->data);
+    }
+    const std::string c = p + "conv.";
+    const HostTensor* p1w = need(c + "pointwise_conv1.weight", {2 * d, d, 1});
+    const HostTensor* p1b = need(c + "pointwise_conv1.bias", {2 * d});
+    const HostTensor* dww = need(c + "depthwise_conv.weight", {d, 1, ks});
+    const HostTensor* dwb = need(c + "depthwise_conv.bias", {d});
+    const HostTensor* bng = need(c + "batch_norm.weight", {d});
+    const HostTensor* bnb = need(c + "batch_norm.bias", {d});
+    const HostTensor* bnm = need(c + "batch_norm.running_mean", {d});
+    const HostTensor* bnv = need(c + "batch_norm.running_var", {d});
+    const HostTensor* p2w = need(c + "pointwise_conv2.weight", {d, d, 1});
+    const HostTensor* p2b = need(c + "pointwise_conv2.bias", {d});
+    if (!missing.empty()) break;
+    {
+      // GLU interleave: accumulator columns in groups of 32 = [16 value channels | their 16 gate channels]
+      std::vector<float> w(static_cast<size_t>(2) * d * d), b(2 * d);
+      for (int col = 0; col < 2 * d; ++col) {
+        const int grp = col / 32, j = col % 32;
+        const int src = (j < 16) ? grp * 16 + j : d + grp * 16 + (j - 16);
+        memcpy(&w[static_cast<size_t>(col) * d], &p1w->data[static_cast<size_t>(src) * d], d * 4);
+        b[col] = p1b->data[src];
+      }
+      lw.w_pw1 = ab.put_mat(w, f32);
+      lw.b_pw1 = ab.put_f32(b);
+      // eval BatchNorm folded into the depth-wise taps (conformer_modules.py:168-175)
+      std::vector<float> taps(static_cast<size_t>(d) * ks), bias(d);
+      for (int ch = 0; ch < d; ++ch) {
+        const double s = static_cast<double>(bng->data[ch]) / sqrt(static_cast<double>(bnv->data[ch]) + 1e-5);
+        for (int k = 0; k < ks; ++k) taps[static_cast<size_t>(ch) * ks + k] = static_cast<float>(dww->data[ch * ks + k] * s);
+        bias[ch] = static_cast<float>((static_cast<double>(dwb->data[ch]) - bnm->data[ch]) * s + bnb->data[ch]);
+      }
+      lw.dw_taps = ab.put_f32(taps);
+      lw.dw_bias = ab.put_f32(bias);
+      lw.w_pw2 = ab.put_mat(p2w->data, f32);
+      lw.b_pw2 = ab.put_f32(p2b->data);
+    }
+  }
+  if (!missing.empty()) return fail(h, CFB_ERR_MISSING_WEIGHT, "cfb_finalize_weights: " + missing);
+  h->w_pos = ab.put_mat(wpos, f32);
+  if (h->has_out_proj) {
+    const HostTensor* w = need("out_proj.weight", {h->d_out, d});
+    const HostTensor* b = need("out_proj.bias", {h->d_out});
+    if (!missing.empty()) return fail(h, CFB_ERR_MISSING_WEIGHT, "cfb_finalize_weights: " + missing);
+    h->w_oproj = ab.put_mat(w->data, f32);
+    h->b_oproj = ab.put_f32(b->data);
+  }
+
+  cudaSetDevice(h->device);
+  if (h->arena) cudaFree(h->arena);
+  h->arena = nullptr;
+  h->arena_bytes = align_up(ab.img.size());
+  cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(h->arena, ab.img.data(), ab.img.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(h, CFB_ERR_CUDA, std::string("cfb_finalize_weights: ") + cudaGetErrorString(e));
+  h->staged.clear();
+  h->finalized = true;
+  return CFB_OK;
+}
+
+int cfb_output_frames(const cfb_handle* h, int T, int* t_out) {
+  if (!h || !t_out || T < 1) return fail(h, CFB_ERR_INVALID_ARG, "cfb_output_frames: bad argument");
+  *t_out = conv_out(conv_out(T));
+  return CFB_OK;
+}
+
+int cfb_workspace_bytes(const cfb_handle* h, int B, int T, size_t* out) {
+  if (!h || !out || B < 1 || T < 1) return fail(h, CFB_ERR_INVALID_ARG, "cfb_workspace_bytes: bad argument");
+  *out = make_plan(h, B, T).total;
+  return CFB_OK;
+}
+
+int cfb_last_launch_count(const cfb_handle* h) { return h ? h->launches : 0; }
+
+int cfb_debug_buffer(const cfb_handle* h, int B, int T, const char* name, size_t* offset, size_t* bytes) {
+  if (!h || !name || !offset || !bytes || B < 1 || T < 1) return fail(h, CFB_ERR_INVALID_ARG, "cfb_debug_buffer: bad argument");
+  const Plan p = make_plan(h, B, T);
+  const size_t e = h->esz();
+  const size_t N = static_cast<size_t>(p.N);
+  const std::string n(name);
+  struct { const char* name; size_t off, bytes; } tab[] = {
+      {"y1", p.y1, static_cast<size_t>(B) * 4 * p.Th * h->Fh * h->C * e},
+      {"y2", p.y2, N * h->F2 * h->C * e},
+      {"x", p.x, N * h->d * 4},
+      {"a", p.a, N * h->d * e},
+      {"h", p.hbuf, N * h->dff * e},
+      {"qkv", p.qkv, N * 4 * h->Dp * e},
+      {"ctx", p.ctx, N * h->Dp * e},
+      {"g", p.g, N * h->d * e},
+      {"c", p.c, N * h->d * e},
+      {"pe", p.pe, static_cast<size_t>(p.P) * h->d * e},
+      {"pos", p.pos, static_cast<size_t>(p.P) * h->L * h->Dp * e},
+  };
+  for (auto& t : tab)
+    if (n == t.name) {
+      *offset = t.off;
+      *bytes = t.bytes;
+      return CFB_OK;
+    }
+  return fail(h, CFB_ERR_INVALID_ARG, "cfb_debug_buffer: unknown buffer " + n);
+}
+
+int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t* lengths, int B, int T, void* encoded,
+                int out_dtype, int32_t* encoded_len, void* workspace, size_t ws_bytes, cfb_stream stream) {
+  if (!h) return CFB_ERR_INVALID_ARG;
+  if (!h->finalized) return fail(h, CFB_ERR_STATE, "cfb_forward: weights are not finalized");
+  if (!feats || !encoded || !encoded_len || !workspace || B < 1 || T < 1)
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward: null pointer or empty batch");
+  if (feats_dtype != CFB_F32 && feats_dtype != CFB_BF16)
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward: feats must be f32 or bf16");
+  if (out_dtype != CFB_F32 && out_dtype != CFB_BF16)
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward: encoded must be f32 or bf16");
+  const Plan pl = make_plan(h, B, T);
+  if (ws_bytes < pl.total || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return fail(h, CFB_ERR_WORKSPACE, "cfb_forward: workspace too small or not 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const bool v = h->validate;
+  const bool abf = !v;  // activations / matrices in bf16
+  const int d = h->d, C = h->C, F2 = h->F2, dff = h->dff, H = h->H, Dp = h->Dp, L = h->L;
+  const int N = pl.N, T2 = pl.T2;
+  std::string err;
+  int launches = 0;
+  float* raw = v ? reinterpret_cast<float*>(ws + pl.raw) : nullptr;
+
+#define CFB_TRY(expr, what)                                                                        \
+  do {                                                                                             \
+    int rc_ = (expr);                                                                              \
+    if (rc_ != 0) {                                                                                \
+      return fail(h, CFB_ERR_CUDA, std::string("cfb_forward: ") + what + " failed: " +             \
+                                       (err.empty() ? cudaGetErrorString((cudaError_t)rc_) : err)); \
+    }                                                                                              \
+  } while (0)
+
+  auto gemm = [&](const void* A, long long lda, const Slot& W, long long ldw, int M, int Nn, int K, int epi,
+                  bool out_bf16, EpiParams ep, const char* what) -> int {
+    GemmDesc g;
+    g.A = A;
+    g.lda = lda;
+    g.W = h->arena + W.off;
+    g.ldw = ldw;
+    g.M = M;
+    g.N = Nn;
+    g.K = K;
+    g.epi = epi;
+    g.out_bf16 = out_bf16;
+    g.ep = ep;
+    int rc;
+    if (v) {
+      rc = launch_gemm_simt(g, raw, st, &err);
+      launches += 2;
+    } else {
+      rc = launch_gemm_tc(g, st, &err);
+      launches += 1;
+    }
+    if (rc != 0 && err.empty()) err = what;
+    return rc;
+  };
+
+  // ---- lengths (subsampling.py:164-171)
+  CFB_TRY(launch_lengths(reinterpret_cast<const long long*>(lengths), encoded_len, B, T, 2, st), "lengths");
+  ++launches;
+  // ---- subsampling: conv 1->C, conv C->C, linear (subsampling.py:172-175)
+  CFB_TRY(launch_subsample_first(feats, feats_dtype == CFB_BF16, h->at<float>(h->sub_w1), h->at<float>(h->sub_b1),
+                                 ws + pl.y1, abf, B, h->F0, T, C, pl.T1, h->F1, pl.Th, h->Fh, st),
+          "subsample conv 0");
+  ++launches;
+  if (v) {
+    CFB_TRY(launch_im2col(reinterpret_cast<const float*>(ws + pl.y1), reinterpret_cast<float*>(ws + pl.cols), B, C,
+                          pl.Th, h->Fh, T2, F2, st),
+            "im2col");
+    ++launches;
+    EpiParams ep;
+    ep.bias = h->at<float>(h->sub_b2);
+    ep.out = ws + pl.y2;
+    ep.ldo = C;
+    CFB_TRY(gemm(ws + pl.cols, 9LL * C, h->sub_w2, 9LL * C, N * F2, C, 9 * C, EPI_RELU, false, ep, "subsample conv 2"),
+            "subsample conv 2");
+  } else {
+    ConvDesc cd;
+    cd.y_in = ws + pl.y1;
+    cd.W = h->arena + h->sub_w2.off;
+    cd.bias = h->at<float>(h->sub_b2);
+    cd.y_out = ws + pl.y2;
+    cd.B = B;
+    cd.C_in = C;
+    cd.C_out = C;
+    cd.Th = pl.Th;
+    cd.Fh = h->Fh;
+    cd.To = T2;
+    cd.Fo = F2;
+    CFB_TRY(launch_conv_tc(cd, st, &err), "subsample conv 2");
+    ++launches;
+  }
+  float* x = reinterpret_cast<float*>(ws + pl.x);
+  {
+    EpiParams ep;
+    ep.bias = h->at<float>(h->sub_b3);
+    ep.out = x;
+    ep.ldo = d;
+    CFB_TRY(gemm(ws + pl.y2, static_cast<long long>(F2) * C, h->sub_w3, static_cast<long long>(F2) * C, N, d, F2 * C,
+                 EPI_LINEAR, false, ep, "pre_encode.out"),
+            "pre_encode.out");
+  }
+  // ---- relative positional table and its per-layer projections (multi_head_attention.py:186-188, 296-316)
+  CFB_TRY(launch_pos_table(ws + pl.pe, abf, h->at<float>(h->div_term), T2, d, st), "pos table");
+  ++launches;
+  {
+    EpiParams ep;
+    ep.out = ws + pl.pos;
+    ep.ldo = static_cast<long long>(L) * Dp;
+    CFB_TRY(gemm(ws + pl.pe, d, h->w_pos, d, pl.P, L * Dp, d, EPI_LINEAR, abf, ep, "linear_pos"), "linear_pos");
+  }
+
+  const int32_t* lens = encoded_len;
+  void* a = ws + pl.a;
+  for (int l = 0; l < L; ++l) {
+    const LayerW& lw = h->layers[l];
+    // -- feed forward 1 (conformer_modules.py:98-101)
+    for (int f = 0; f < 2; ++f) {
+      if (f == 1) {
+        // -- self attention (conformer_modules.py:103-110)
+        CFB_TRY(launch_layernorm(x, h->at<float>(lw.ln_g[1]), h->at<float>(lw.ln_b[1]), a, abf, N, d, nullptr, 1, st),
+                "norm_self_att");
+        ++launches;
+        EpiParams ep;
+        ep.bias = h->at<float>(lw.b_qkv);
+        ep.bias2 = h->at<float>(lw.b_qv);
+        ep.out = ws + pl.qkv;
+        ep.ldo = 4LL * Dp;
+        ep.qkv_dp = Dp;
+        CFB_TRY(gemm(a, d, lw.w_qkv, d, N, 3 * Dp, d, EPI_QKV, abf, ep, "qkv projection"), "qkv projection");
+        AttnDesc ad;
+        ad.qkv = ws + pl.qkv;
+        ad.pos = ws + pl.pos + static_cast<size_t>(l) * Dp * h->esz();
+        ad.ld_pos = static_cast<long long>(L) * Dp;
+        ad.ctx = ws + pl.ctx;
+        ad.lens = lens;
+        ad.B = B;
+        ad.T = T2;
+        ad.H = H;
+        ad.dk = h->dk;
+        ad.dkp = h->dkp;
+        CFB_TRY(v ? launch_attn_simt(ad, st, &err) : launch_attn_tc(ad, st, &err), "rel-pos attention");
+        ++launches;
+        EpiParams eo;
+        eo.bias = h->at<float>(lw.b_out);
+        eo.out = x;
+        eo.ldo = d;
+        eo.alpha = 1.f;
+        CFB_TRY(gemm(ws + pl.ctx, Dp, lw.w_out, Dp, N, d, Dp, EPI_RESID, false, eo, "linear_out"), "linear_out");
+        // -- convolution module (conformer_modules.py:112-114, 160-180)
+        CFB_TRY(launch_layernorm(x, h->at<float>(lw.ln_g[2]), h->at<float>(lw.ln_b[2]), a, abf, N, d, nullptr, 1, st),
+                "norm_conv");
+        ++launches;
+        EpiParams eg;
+        eg.bias = h->at<float>(lw.b_pw1);
+        eg.out = ws + pl.g;
+        eg.ldo = d;
+        eg.lens = lens;
+        eg.frames_per_seq = T2;
+        CFB_TRY(gemm(a, d, lw.w_pw1, d, N, 2 * d, d, EPI_GLU, abf, eg, "pointwise_conv1+glu"), "pointwise_conv1+glu");
+        CFB_TRY(launch_depthwise(ws + pl.g, h->at<float>(lw.dw_taps), h->at<float>(lw.dw_bias), ws + pl.c, abf, B, T2,
+                                 d, h->ksize, st),
+                "depthwise conv");
+        ++launches;
+        EpiParams e2;
+        e2.bias = h->at<float>(lw.b_pw2);
+        e2.out = x;
+        e2.ldo = d;
+        e2.alpha = 1.f;
+        CFB_TRY(gemm(ws + pl.c, d, lw.w_pw2, d, N, d, d, EPI_RESID, false, e2, "pointwise_conv2"), "pointwise_conv2");
+      }
+      const int ln = f == 0 ? 0 : 3;
+      CFB_TRY(launch_layernorm(x, h->at<float>(lw.ln_g[ln]), h->at<float>(lw.ln_b[ln]), a, abf, N, d, nullptr, 1, st),
+              "norm_feed_forward");
+      ++launches;
+      EpiParams e1;
+      e1.bias = h->at<float>(lw.ff_b1[f]);
+      e1.out = ws + pl.hbuf;
+      e1.ldo = dff;
+      CFB_TRY(gemm(a, d, lw.ff_w1[f], d, N, dff, d, EPI_SWISH, abf, e1, "linear1+swish"), "linear1+swish");
+      EpiParams e2;
+      e2.bias = h->at<float>(lw.ff_b2[f]);
+      e2.out = x;
+      e2.ldo = d;
+      e2.alpha = 0.5f;  // fc_factor (conformer_modules.py:57,101,118)
+      CFB_TRY(gemm(ws + pl.hbuf, dff, lw.ff_w2[f], dff, N, d, dff, EPI_RESID, false, e2, "linear2"), "linear2");
+    }
+    // -- norm_out (conformer_modules.py:120); the last one writes the result
+    const bool last = (l == L - 1);
+    if (last && !h->has_out_proj) {
+      CFB_TRY(launch_layernorm(x, h->at<float>(lw.ln_g[4]), h->at<float>(lw.ln_b[4]), encoded, out_dtype == CFB_BF16, N,
+                               d, lens, T2, st),
+              "norm_out");
+    } else if (last) {
+      CFB_TRY(launch_layernorm(x, h->at<float>(lw.ln_g[4]), h->at<float>(lw.ln_b[4]), a, abf, N, d, nullptr, 1, st),
+              "norm_out");
+    } else {
+      CFB_TRY(launch_layernorm(x, h->at<float>(lw.ln_g[4]), h->at<float>(lw.ln_b[4]), x, false, N, d, nullptr, 1, st),
+              "norm_out");
+    }
+    ++launches;
+  }
+  if (h->has_out_proj) {  // conformer_encoder.py:277-278
+    EpiParams ep;
+    ep.bias = h->at<float>(h->b_oproj);
+    ep.out = encoded;
+    ep.ldo = h->d_out;
+    ep.lens = lens;
+    ep.frames_per_seq = T2;
+    CFB_TRY(gemm(a, d, h->w_oproj, d, N, h->d_out, d, EPI_LINEAR, out_dtype == CFB_BF16, ep, "out_proj"), "out_proj");
+  }
+#undef CFB_TRY
+  h->launches = launches;
+  return CFB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel-level entry points
+namespace {
+std::string g_op_error;
+int op_fail(int rc, const std::string& err) {
+  g_op_error = err.empty() ? std::string(cudaGetErrorString((cudaError_t)rc)) : err;
+  g_create_error = g_op_error;  // cfb_last_error(NULL) reports handle-less failures
+  return CFB_ERR_CUDA;
+}
+}  // namespace
+
+int cfb_op_gemm(int use_tc, int epilogue, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                const float* bias2, int M, int N, int K, void* out, int64_t ldo, int out_dtype, float alpha,
+                const int32_t* lens, int frames_per_seq, int qkv_dp, float* scratch, cfb_stream stream) {
+  GemmDesc g;
+  g.A = A;
+  g.lda = lda;
+  g.W = W;
+  g.ldw = ldw;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.epi = epilogue;
+  g.out_bf16 = out_dtype == CFB_BF16;
+  g.ep.bias = bias;
+  g.ep.bias2 = bias2;
+  g.ep.out = out;
+  g.ep.ldo = ldo;
+  g.ep.alpha = alpha;
+  g.ep.lens = lens;
+  g.ep.frames_per_seq = frames_per_seq > 0 ? frames_per_seq : 1;
+  g.ep.qkv_dp = qkv_dp;
+  std::string err;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = use_tc ? launch_gemm_tc(g, st, &err) : launch_gemm_simt(g, scratch, st, &err);
+  return rc == 0 ? CFB_OK : op_fail(rc, err);
+}
+
+int cfb_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows, int d,
+                     const int32_t* lens, int frames_per_seq, cfb_stream stream) {
+  int rc = launch_layernorm(x, gamma, beta, out, out_dtype == CFB_BF16, rows, d, lens, frames_per_seq > 0 ? frames_per_seq : 1,
+                            reinterpret_cast<cudaStream_t>(stream));
+  return rc == 0 ? CFB_OK : op_fail(rc, rc == -1 ? "layernorm: d must be a multiple of 4 and <= 1024" : "");
+}
+
+int cfb_op_depthwise(const void* x, const float* taps, const float* bias, void* out, int dtype, int B, int T, int d,
+                     int ksize, cfb_stream stream) {
+  int rc = launch_depthwise(x, taps, bias, out, dtype == CFB_BF16, B, T, d, ksize, reinterpret_cast<cudaStream_t>(stream));
+  return rc == 0 ? CFB_OK : op_fail(rc, rc == -1 ? "depthwise: ksize must be odd <= 31 and d even" : "");
+}
+
+int cfb_op_rel_attention(int use_tc, const void* qkv, const void* pos, int64_t ld_pos, void* ctx, const int32_t* lens,
+                         int B, int T, int H, int dk, int dkp, cfb_stream stream) {
+  AttnDesc a;
+  a.qkv = qkv;
+  a.pos = pos;
+  a.ld_pos = ld_pos;
+  a.ctx = ctx;
+  a.lens = lens;
+  a.B = B;
+  a.T = T;
+  a.H = H;
+  a.dk = dk;
+  a.dkp = dkp;
+  std::string err;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = use_tc ? launch_attn_tc(a, st, &err) : launch_attn_simt(a, st, &err);
+  return rc == 0 ? CFB_OK : op_fail(rc, err);
+}
+
+int cfb_op_lengths(const int64_t* lengths, int32_t* out, int B, int T_full, int n_stages, cfb_stream stream) {
+  int rc = launch_lengths(reinterpret_cast<const long long*>(lengths), out, B, T_full, n_stages,
+                          reinterpret_cast<cudaStream_t>(stream));
+  return rc == 0 ? CFB_OK : op_fail(rc, "");
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+// tcgen05 GEMM for sm_100a:  D (M x N) = A (M x K, bf16) * W^T (W: N x K, bf16), fp32 accumulation in TMEM,
+// fused epilogue (epilogue.cuh).  Also the implicit-GEMM form of the strided 3x3 subsampling convolution.
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0      TMA producer (one lane): A and W tiles, 128-byte swizzle, STAGES-deep mbarrier ring
+//   warp 1      MMA issuer (one lane): tcgen05.mma cta_group::1, 128 x BN x 16 per instruction, BLOCK_K = 64
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (thread = output row), bias / activation / residual, 16-byte stores
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop
+// of tile i+1.  M/N/K tails are handled by TMA zero fill on the load side and predication on the store side.
+#include <stdio.h>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace cfb {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int kThreads = 192;
+
+struct TcParams {
+  int num_tiles;
+  int num_n_tiles;
+  int num_k_blocks;
+  // implicit-GEMM convolution (CONV = true)
+  int conv_cchunks;   // k-blocks per filter tap = ceil(C_in / 64)
+  int conv_cin;
+  int conv_tblocks;   // output tiles per sequence along time (32 frames each)
+  int conv_fblocks;   // output tiles along frequency (4 bins each)
+  int conv_To, conv_Fo;
+  EpiParams ep;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BN, int STAGES, int EPI, typename TOut, bool CONV>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;  // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = 2 * BN;  // 128 / 256 / 512: a power of two >= 32
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmA);
+      ptx::prefetch_tmap(&tmB);
+      for (int s = 0; s < STAGES; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        ptx::mbar_init(&acc_full[b], 1);
+        ptx::mbar_init(&acc_empty[b], 128);
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.num_n_tiles;
+        const int m_blk = tile / p.num_n_tiles;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          if constexpr (CONV) {
+            const int fb = m_blk % p.conv_fblocks;
+            const int tb = (m_blk / p.conv_fblocks) % p.conv_tblocks;
+            const int b = m_blk / (p.conv_fblocks * p.conv_tblocks);
+            const int tap = kb / p.conv_cchunks;
+            const int cc = kb - tap * p.conv_cchunks;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            // input index 2*o + k - 1: k = 1 -> even plane, same index; k = 0 -> odd plane, index o-1; k = 2 -> odd, o
+            const int plane = ((kh == 1) ? 0 : 2) + ((kw == 1) ? 0 : 1);
+            const int tcoord = tb * 32 - (kh == 0 ? 1 : 0);
+            const int fcoord = fb * 4 - (kw == 0 ? 1 : 0);
+            ptx::tma_load_5d(sa, &tmA, &full_bar[stage], cc * 64, fcoord, tcoord, plane, b);
+            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.conv_cin + cc * 64, n_blk * BN);
+          } else {
+            ptx::tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
+            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], kb * kBlockK, n_blk * BN);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+          const uint64_t da = ptx::make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t db = ptx::make_sdesc_sw128(sa + L::kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 bytes per K step inside the 128-byte swizzle row (descriptor address field is in 16-byte units)
+            ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::tc_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int quarter = warp & 3;  // TMEM lanes this warp may read: [32*quarter, +32)
+    const int row_in_tile = quarter * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int n_blk = tile % p.num_n_tiles;
+      const int m_blk = tile / p.num_n_tiles;
+      long long out_row;
+      bool row_ok;
+      if constexpr (CONV) {
+        const int fb = m_blk % p.conv_fblocks;
+        const int tb = (m_blk / p.conv_fblocks) % p.conv_tblocks;
+        const int b = m_blk / (p.conv_fblocks * p.conv_tblocks);
+        const int t = tb * 32 + (row_in_tile >> 2);
+        const int f = fb * 4 + (row_in_tile & 3);
+        row_ok = (t < p.conv_To) && (f < p.conv_Fo);
+        out_row = (static_cast<long long>(b) * p.conv_To + t) * p.conv_Fo + f;
+      } else {
+        out_row = static_cast<long long>(m_blk) * kBlockM + row_in_tile;
+        row_ok = out_row < p.ep.M;
+      }
+      ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_x32(t_addr + c * 32, v);
+        ptx::tc_wait_ld();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && col0 < p.ep.N) {
+          float acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+          epi_apply<EPI, TOut>(p.ep, out_row, col0, acc);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&acc_empty[buf]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int STAGES, int EPI, typename TOut, bool CONV>
+int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st,
+                    std::string* err) {
+  using L = SmemLayout<BN, STAGES>;
+  auto kern = gemm_tc_kernel<BN, STAGES, EPI, TOut, CONV>;
+  static bool configured[64] = {};  // per instantiation and device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("cudaFuncSetAttribute(gemm_tc): ") + cudaGetErrorString(e);
+      return static_cast<int>(e);
+    }
+    configured[dev & 63] = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  kern<<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("gemm_tc launch: ") + cudaGetErrorString(e);
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+template <int BN, int STAGES, bool CONV>
+int dispatch_epi(int epi, bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p,
+                 cudaStream_t st, std::string* err) {
+  if constexpr (CONV) {
+    return launch_instance<BN, STAGES, EPI_RELU, bf16, true>(tmA, tmB, p, st, err);
+  } else {
+    switch (epi) {
+      case EPI_LINEAR:
+        return out_bf16 ? launch_instance<BN, STAGES, EPI_LINEAR, bf16, false>(tmA, tmB, p, st, err)
+                        : launch_instance<BN, STAGES, EPI_LINEAR, float, false>(tmA, tmB, p, st, err);
+      case EPI_SWISH:
+        return launch_instance<BN, STAGES, EPI_SWISH, bf16, false>(tmA, tmB, p, st, err);
+      case EPI_RELU:
+        return launch_instance<BN, STAGES, EPI_RELU, bf16, false>(tmA, tmB, p, st, err);
+      case EPI_RESID:
+        return launch_instance<BN, STAGES, EPI_RESID, float, false>(tmA, tmB, p, st, err);
+      case EPI_QKV:
+        return launch_instance<BN, STAGES, EPI_QKV, bf16, false>(tmA, tmB, p, st, err);
+      case EPI_GLU:
+        return launch_instance<BN, STAGES, EPI_GLU, bf16, false>(tmA, tmB, p, st, err);
+      default:
+        if (err) *err = "gemm_tc: unknown epilogue";
+        return -1;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
+  if ((g.lda % 8) || (g.ldw % 8) || (g.K % 8)) {
+    if (err) *err = "gemm_tc: K and leading dimensions must be multiples of 8 (16-byte TMA strides)";
+    return -1;
+  }
+  // tile width: 256 for wide outputs when it does not hurt the wave count, else 128
+  const int m_tiles = (g.M + kBlockM - 1) / kBlockM;
+  int bn = 128;
+  if (g.N >= 1024 && g.N % 256 == 0 && g.epi != EPI_GLU && g.epi != EPI_QKV) bn = 256;
+  const int n_tiles = (g.N + bn - 1) / bn;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(g.K), static_cast<uint64_t>(g.M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(g.lda) * 2};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    if (!encode_tmap_bf16(&tmA, g.A, 2, dims, strides, box, err)) return -1;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(g.K), static_cast<uint64_t>(g.N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(g.ldw) * 2};
+    uint32_t box[2] = {kBlockK, static_cast<uint32_t>(bn)};
+    if (!encode_tmap_bf16(&tmB, g.W, 2, dims, strides, box, err)) return -1;
+  }
+  TcParams p{};
+  p.num_n_tiles = n_tiles;
+  p.num_tiles = m_tiles * n_tiles;
+  p.num_k_blocks = (g.K + kBlockK - 1) / kBlockK;
+  p.ep = g.ep;
+  p.ep.M = g.M;
+  p.ep.N = g.N;
+  if (bn == 256) return dispatch_epi<256, 4, false>(g.epi, g.out_bf16, tmA, tmB, p, st, err);
+  return dispatch_epi<128, 6, false>(g.epi, g.out_bf16, tmA, tmB, p, st, err);
+}
+
+int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err) {
+  if (c.C_in % 8 || c.C_out % 8) {
+    if (err) *err = "conv_tc: channel counts must be multiples of 8";
+    return -1;
+  }
+  CUtensorMap tmA, tmB;
+  {
+    // [B][plane 4][Th][Fh][C] -> dims innermost first
+    uint64_t dims[5] = {static_cast<uint64_t>(c.C_in), static_cast<uint64_t>(c.Fh), static_cast<uint64_t>(c.Th), 4,
+                        static_cast<uint64_t>(c.B)};
+    uint64_t s1 = static_cast<uint64_t>(c.C_in) * 2;
+    uint64_t strides[4] = {s1, s1 * c.Fh, s1 * c.Fh * c.Th, s1 * c.Fh * c.Th * 4};
+    uint32_t box[5] = {64, 4, 32, 1, 1};
+    if (!encode_tmap_bf16(&tmA, c.y_in, 5, dims, strides, box, err)) return -1;
+  }
+  const int K = 9 * c.C_in;
+  const int bn = 128;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(c.C_out)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {kBlockK, static_cast<uint32_t>(bn)};
+    if (!encode_tmap_bf16(&tmB, c.W, 2, dims, strides, box, err)) return -1;
+  }
+  TcParams p{};
+  p.conv_cin = c.C_in;
+  p.conv_cchunks = (c.C_in + 63) / 64;
+  p.conv_tblocks = (c.To + 31) / 32;
+  p.conv_fblocks = (c.Fo + 3) / 4;
+  p.conv_To = c.To;
+  p.conv_Fo = c.Fo;
+  p.num_n_tiles = (c.C_out + bn - 1) / bn;
+  p.num_tiles = c.B * p.conv_tblocks * p.conv_fblocks * p.num_n_tiles;
+  p.num_k_blocks = 9 * p.conv_cchunks;
+  p.ep.bias = c.bias;
+  p.ep.out = c.y_out;
+  p.ep.ldo = c.C_out;
+  p.ep.M = c.B * c.To * c.Fo;
+  p.ep.N = c.C_out;
+  return dispatch_epi<128, 6, true>(EPI_RELU, true, tmA, tmB, p, st, err);
+}
+
+}  // namespace cfb

@@ -1,0 +1,82 @@
+"""GPU: relative-position attention.  The CUDA-core validation kernel is checked against a torch restatement of
+multi_head_attention.py:195-210 / :104-113 (pad/view rel_shift included); the fused tcgen05 kernel is checked against
+both on bf16-rounded inputs."""
+import math
+
+import pytest
+import torch
+
+from gpu_util import err_stats, op_attention
+
+pytestmark = pytest.mark.gpu
+
+
+def torch_reference(qu, qv, k, v, p, lens):
+    """qu,qv,k,v: (B,H,T,dk); p: (H,2T-1,dk); returns ctx (B,T,H,dk) with the reference's masking semantics."""
+    B, H, T, dk = qu.shape
+    ac = qu @ k.transpose(-1, -2)
+    bd = qv @ p.transpose(-1, -2).unsqueeze(0)  # (B,H,T,2T-1)
+    bd = torch.nn.functional.pad(bd, (1, 0)).view(B, H, -1, T)[:, :, 1:].view(B, H, T, 2 * T - 1)[..., :T]
+    scores = (ac + bd) / math.sqrt(dk)
+    valid = torch.arange(T, device=qu.device)[None] < lens[:, None]
+    mask = ~(valid[:, :, None] & valid[:, None, :]).unsqueeze(1)
+    scores = scores.masked_fill(mask, -10000.0)
+    attn = torch.softmax(scores, -1).masked_fill(mask, 0.0)
+    return (attn @ v).permute(0, 2, 1, 3)
+
+
+def make_case(B, T, H, dk, lens, seed, dtype, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dkp, Dp = 64, H * 64
+    parts = [torch.randn(B, H, T, dk, generator=g, device="cuda") * scale for _ in range(4)]
+    p = torch.randn(H, 2 * T - 1, dk, generator=g, device="cuda") * scale
+    parts = [t.to(dtype).float() for t in parts]
+    p = p.to(dtype).float()
+    qkv = torch.zeros(B * T, 4 * Dp, device="cuda")
+    for i, t in enumerate(parts):
+        blk = torch.zeros(B, T, H, dkp, device="cuda")
+        blk[..., :dk] = t.permute(0, 2, 1, 3)
+        qkv[:, i * Dp:(i + 1) * Dp] = blk.reshape(B * T, Dp)
+    n_layers_pad = 2  # the kernel reads this layer's columns out of a wider buffer
+    pos = torch.full((2 * T - 1, n_layers_pad * Dp), 7.0, device="cuda")
+    pblk = torch.zeros(2 * T - 1, H, dkp, device="cuda")
+    pblk[..., :dk] = p.permute(1, 0, 2)
+    pos[:, Dp:] = pblk.reshape(2 * T - 1, Dp)
+    lens_t = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    want = torch_reference(*parts, p, lens_t)  # (B,T,H,dk)
+    return qkv, pos, lens_t, want, Dp
+
+
+CASES = [  # B, T, H, dk, lens
+    (2, 21, 4, 16, [21, 5]),
+    (2, 50, 4, 44, [50, 33]),
+    (1, 128, 2, 64, [128]),
+    (2, 200, 8, 64, [200, 77]),
+    (3, 333, 2, 32, [333, 64, 0]),
+]
+
+
+@pytest.mark.parametrize("B,T,H,dk,lens", CASES)
+def test_simt_attention_matches_reference_semantics(B, T, H, dk, lens):
+    qkv, pos, lens_t, want, Dp = make_case(B, T, H, dk, lens, 1, torch.float32)
+    ctx = torch.full((B * T, Dp), float("nan"), device="cuda")
+    op_attention(False, qkv, pos[:, Dp:], ctx, lens_t, B, T, H, dk)
+    got = ctx.view(B, T, H, 64)
+    st = err_stats(got[..., :dk], want)
+    assert st["nan"] == 0 and st["max_abs"] < 2e-5, st
+    assert torch.all(got[..., dk:] == 0)
+    for b, n in enumerate(lens):  # padded query rows: exactly zero
+        assert torch.all(got[b, n:] == 0)
+
+
+@pytest.mark.parametrize("B,T,H,dk,lens", CASES + [(1, 700, 1, 64, [700]), (2, 129, 2, 64, [129, 128])])
+def test_tc_attention_matches_reference(B, T, H, dk, lens):
+    qkv, pos, lens_t, want, Dp = make_case(B, T, H, dk, lens, 2, torch.bfloat16)
+    ctx = torch.full((B * T, Dp), float("nan"), device="cuda", dtype=torch.bfloat16)
+    op_attention(True, qkv.bfloat16(), pos.bfloat16()[:, Dp:], ctx, lens_t, B, T, H, dk)
+    got = ctx.float().view(B, T, H, 64)
+    st = err_stats(got[..., :dk], want)
+    # bf16 probabilities and bf16 output rounding: ~3 significant digits
+    assert st["nan"] == 0 and st["rel_l2"] < 1.5e-2 and st["max_abs"] < 6e-2, st
+    for b, n in enumerate(lens):
+        assert torch.all(got[b, n:] == 0)

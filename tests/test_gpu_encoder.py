@@ -1,0 +1,179 @@
+"""GPU: end-to-end parity of the CUDA encoder (through conformer_nemo_b200.ConformerEncoder -> ctypes -> libcfb.so)
+against the oracle and the committed reference golden vectors.
+
+Tolerances (BASELINE.json north_star): encoded_len bit-exact; on valid frames rel-L2 <= 1e-2 and max-abs <= 5e-2 in
+bf16, <= 1e-4 in the fp32 validation mode; CTC greedy argmax agreement >= 99 %.
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import conformer_nemo_b200 as cn
+from oracle import conformer_oracle as oc
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if "lengths" not in p)
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    cfg = oc.EncoderConfig(**meta["config"])
+    stored = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w:")}
+    sd = stored if stored else oc.random_state_dict(cfg, meta["weight_seed"])
+    return z, cfg, sd
+
+
+def build(cfg: oc.EncoderConfig, sd, precision):
+    enc = cn.ConformerEncoder(feat_in=cfg.feat_in, n_layers=cfg.n_layers, d_model=cfg.d_model, feat_out=cfg.feat_out,
+                              subsampling_conv_channels=cfg.subsampling_conv_channels,
+                              ff_expansion_factor=cfg.ff_expansion_factor, n_heads=cfg.n_heads, xscaling=cfg.xscaling,
+                              conv_kernel_size=cfg.conv_kernel_size, precision=precision)
+    missing, unexpected = enc.load_state_dict(sd, strict=False)
+    assert not unexpected and all("num_batches_tracked" in m for m in missing), (missing, unexpected)
+    return enc.cuda().eval()
+
+
+def valid_mask(enc_len, t_out):
+    return (torch.arange(t_out)[None, :] < enc_len.cpu()[:, None].long())
+
+
+def compare(got, want, enc_len):
+    """got/want (B, D, T') on cpu; metrics over valid frames only."""
+    m = valid_mask(enc_len, want.shape[2])[:, None, :].expand_as(want)
+    g, w = got.double()[m], want.double()[m]
+    return dict(rel_l2=float((g - w).norm() / w.norm()), max_abs=float((g - w).abs().max()),
+                nan=int(torch.isnan(got).sum()))
+
+
+def ctc_agreement(got, want, enc_len, seed=0, vocab=129):
+    """ConvASRDecoder-equivalent 1x1 conv head (conv_asr.py:437-444) applied in fp32 to both outputs."""
+    gen = torch.Generator().manual_seed(seed)
+    d = want.shape[1]
+    bound = (6.0 / (d + vocab)) ** 0.5  # xavier_uniform
+    w = (torch.rand(vocab, d, generator=gen) * 2 - 1) * bound
+    a = torch.einsum("vd,bdt->bvt", w, got.float()).argmax(1)
+    b = torch.einsum("vd,bdt->bvt", w, want.float()).argmax(1)
+    m = valid_mask(enc_len, want.shape[2])
+    return float((a == b)[m].float().mean())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_validation_mode_matches_reference_golden(name):
+    z, cfg, sd = load_case(name)
+    enc = build(cfg, sd, "fp32_validate")
+    x = torch.from_numpy(z["audio_signal"]).cuda()
+    length = torch.from_numpy(z["length"]).cuda() if bool(z["has_length"]) else None
+    y, ylen = enc(audio_signal=x, length=length)
+    torch.cuda.synchronize()
+    assert ylen.dtype == torch.int32 and np.array_equal(ylen.cpu().numpy(), z["encoded_len"])
+    assert tuple(y.shape) == z["encoded"].shape and not y.is_contiguous() and y.transpose(1, 2).is_contiguous()
+    st = compare(y.cpu(), torch.from_numpy(z["encoded"]), ylen)
+    assert st["nan"] == 0 and st["rel_l2"] < 1e-4 and st["max_abs"] < 1e-4 * max(1.0, float(np.abs(z["encoded"]).max())), st
+    # frames beyond encoded_len are written as zeros
+    m = valid_mask(ylen, y.shape[2])[:, None, :].expand_as(y)
+    assert torch.all(y.cpu()[~m] == 0)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_bf16_tensor_core_path_matches_reference_golden(name):
+    z, cfg, sd = load_case(name)
+    enc = build(cfg, sd, "bf16")
+    x = torch.from_numpy(z["audio_signal"]).cuda()
+    length = torch.from_numpy(z["length"]).cuda() if bool(z["has_length"]) else None
+    y, ylen = enc(audio_signal=x, length=length)
+    torch.cuda.synchronize()
+    assert np.array_equal(ylen.cpu().numpy(), z["encoded_len"])
+    want = torch.from_numpy(z["encoded"])
+    st = compare(y.cpu(), want, ylen)
+    assert st["nan"] == 0 and st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, st
+    assert enc.last_launch_count() > 0
+
+
+def test_intermediates_tc_vs_validation_single_layer():
+    """Stage-by-stage comparison of the two CUDA paths on a 1-layer model (localises a faulty kernel)."""
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=1, d_model=176, n_heads=4)
+    sd = oc.random_state_dict(cfg, 21)
+    x, length = oc.synthetic_batch(2, 80, 203, [203, 150], seed=5)
+    outs = {}
+    for prec in ("fp32_validate", "bf16"):
+        enc = build(cfg, sd, prec)
+        enc(audio_signal=x.cuda(), length=length.cuda())
+        torch.cuda.synchronize()
+        dt = torch.float32 if prec == "fp32_validate" else torch.bfloat16
+        outs[prec] = {n: enc.debug_buffer(2, 203, n).clone().view(dt).float().cpu()
+                      for n in ("y1", "y2", "pe", "pos", "qkv", "ctx", "g", "c", "h")}
+    report = {}
+    for n in outs["bf16"]:
+        a, b = outs["bf16"][n].double(), outs["fp32_validate"][n].double()
+        report[n] = float((a - b).norm() / b.norm().clamp_min(1e-30))
+    assert all(v < 2e-2 for v in report.values()), report
+
+
+def test_large_config_mixed_lengths_against_oracle():
+    """Conformer-L shaped layers (d=512, H=8, dk=64), 3 layers, mixed lengths incl. a very short row; oracle on CPU."""
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=3, d_model=512, n_heads=8)
+    sd = oc.random_state_dict(cfg, 31)
+    x, length = oc.synthetic_batch(4, 80, 1037, [1037, 640, 333, 9], seed=7)
+    want, want_len = oc.encoder_forward(sd, cfg, x, length)
+    for prec, tol_l2, tol_abs in (("fp32_validate", 1e-4, 1e-3), ("bf16", 1e-2, 5e-2)):
+        enc = build(cfg, sd, prec)
+        y, ylen = enc(audio_signal=x.cuda(), length=length.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(ylen.cpu(), want_len)
+        st = compare(y.cpu(), want, ylen)
+        assert st["nan"] == 0 and st["rel_l2"] <= tol_l2 and st["max_abs"] <= tol_abs, (prec, st)
+        agree = ctc_agreement(y.cpu(), want, ylen)
+        assert agree >= 0.99, (prec, agree)
+
+
+def test_bf16_input_and_output_dtypes_and_repeatability():
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=2, d_model=256, n_heads=4)
+    sd = oc.random_state_dict(cfg, 41)
+    x, length = oc.synthetic_batch(3, 80, 400, [400, 399, 120], seed=9)
+    enc = build(cfg, sd, "bf16")
+    y1, l1 = enc(audio_signal=x.cuda(), length=length.cuda())
+    y2, l2 = enc(audio_signal=x.cuda(), length=length.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2) and torch.equal(l1, l2)  # deterministic: no atomics, fixed schedule
+    y3, _ = enc(audio_signal=x.cuda(), length=length.cuda(), out_dtype=torch.bfloat16)
+    assert y3.dtype == torch.bfloat16
+    assert float((y3.float() - y1).abs().max()) < 4e-2
+    # int32 lengths are accepted like the reference accepts any integer dtype
+    y4, l4 = enc(audio_signal=x.cuda(), length=length.int().cuda())
+    assert torch.equal(l4, l1) and torch.equal(y4, y1)
+    # different batch shape on the same handle (workspace regrows)
+    xb, lb = oc.synthetic_batch(5, 80, 777, [777, 700, 512, 300, 41], seed=10)
+    wb, wl = oc.encoder_forward(sd, cfg, xb, lb)
+    yb, ylb = enc(audio_signal=xb.cuda(), length=lb.cuda())
+    assert torch.equal(ylb.cpu(), wl)
+    st = compare(yb.cpu(), wb, ylb)
+    assert st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, st
+
+
+def test_cuda_graph_capture_of_forward():
+    """cfb_forward is enqueue-only (no allocation / sync), so the whole forward can be captured in a CUDA graph."""
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=2, d_model=256, n_heads=4)
+    sd = oc.random_state_dict(cfg, 51)
+    x, length = oc.synthetic_batch(2, 80, 320, [320, 200], seed=11)
+    enc = build(cfg, sd, "bf16")
+    xs, ls = x.cuda(), length.cuda()
+    y_ref, _ = enc(audio_signal=xs, length=ls)  # warm-up: allocates workspace, packs weights
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y_cap, len_cap = enc(audio_signal=xs, length=ls)
+    xs.copy_(torch.roll(x, 1, 0).cuda())
+    ls.copy_(torch.roll(length, 1, 0).cuda())
+    graph.replay()
+    torch.cuda.synchronize()
+    y_new, len_new = enc(audio_signal=xs, length=ls)
+    torch.cuda.synchronize()
+    assert torch.equal(len_cap, len_new)
+    assert float((y_cap - y_new).abs().max()) == 0.0
+    assert float((y_cap - y_ref).abs().max()) > 0.0
