@@ -22,7 +22,8 @@ STATUS_NAMES = {1: "invalid argument", 2: "unsupported configuration", 3: "missi
 # every symbol include/cfb.h declares (tests check that the built library exports each of them)
 SYMBOLS = [
     "cfb_create", "cfb_destroy", "cfb_last_error", "cfb_set_weight", "cfb_finalize_weights", "cfb_output_frames",
-    "cfb_workspace_bytes", "cfb_forward", "cfb_debug_buffer", "cfb_last_launch_count", "cfb_op_gemm",
+    "cfb_workspace_bytes", "cfb_forward", "cfb_debug_buffer", "cfb_set_profiling", "cfb_profile_report",
+    "cfb_last_launch_count", "cfb_op_gemm",
     "cfb_op_layernorm", "cfb_op_depthwise", "cfb_op_rel_attention", "cfb_op_lengths",
 ]
 
@@ -65,6 +66,8 @@ def load_library() -> ctypes.CDLL:
         lib.cfb_forward.argtypes = [vp, vp, i32, vp, i32, i32, vp, i32, vp, vp, sz, vp]
         lib.cfb_debug_buffer.argtypes = [vp, i32, i32, ctypes.c_char_p, ctypes.POINTER(sz), ctypes.POINTER(sz)]
         lib.cfb_last_launch_count.argtypes = [vp]
+        lib.cfb_set_profiling.argtypes = [vp, i32]
+        lib.cfb_profile_report.argtypes = [vp, ctypes.c_char_p, sz]
         lib.cfb_op_gemm.argtypes = [i32, i32, vp, i64, vp, i64, vp, vp, i32, i32, i32, vp, i64, i32, ctypes.c_float,
                                     vp, i32, i32, vp, vp]
         lib.cfb_op_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, i32, vp]

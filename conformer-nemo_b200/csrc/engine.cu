@@ -63,6 +63,15 @@ struct cfb_handle {
   std::vector<LayerW> layers;
   int launches = 0;
   mutable std::string err;
+  // optional per-launch event timing
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Rec {
+    const char* label;
+    size_t e0, e1;
+  };
+  std::vector<Rec> recs;
 
   size_t esz() const { return validate ? 4 : 2; }  // bytes per activation / matrix element
   template <typename T>
@@ -231,10 +240,9 @@ int cfb_create(const cfb_config* cfg, int device, cfb_handle** out) {
 
 void cfb_destroy(cfb_handle* h) {
   if (!h) return;
-  if (h->arena) {
-    cudaSetDevice(h->device);
-    cudaFree(h->arena);
-  }
+  cudaSetDevice(h->device);
+  if (h->arena) cudaFree(h->arena);
+  for (auto& e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
 
@@ -487,6 +495,49 @@ int cfb_workspace_bytes(const cfb_handle* h, int B, int T, size_t* out) {
 
 int cfb_last_launch_count(const cfb_handle* h) { return h ? h->launches : 0; }
 
+int cfb_set_profiling(cfb_handle* h, int on) {
+  if (!h) return CFB_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (on && h->ev_pool.empty()) {
+    h->ev_pool.resize(16384);
+    for (auto& e : h->ev_pool)
+      if (cudaEventCreate(&e) != cudaSuccess) return fail(h, CFB_ERR_CUDA, "cfb_set_profiling: cudaEventCreate failed");
+  }
+  h->profiling = on != 0;
+  h->ev_used = 0;
+  h->recs.clear();
+  return CFB_OK;
+}
+
+int cfb_profile_report(cfb_handle* h, char* buf, size_t cap) {
+  if (!h || !buf || cap == 0) return CFB_ERR_INVALID_ARG;
+  std::map<std::string, std::pair<int, double>> agg;
+  std::vector<std::string> order;
+  for (const auto& r : h->recs) {
+    cudaEventSynchronize(h->ev_pool[r.e1]);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[r.e0], h->ev_pool[r.e1]) != cudaSuccess) continue;
+    auto it = agg.find(r.label);
+    if (it == agg.end()) {
+      order.push_back(r.label);
+      agg[r.label] = {1, ms};
+    } else {
+      it->second.first += 1;
+      it->second.second += ms;
+    }
+  }
+  std::string out;
+  for (const auto& k : order) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s\t%d\t%.6f\n", k.c_str(), agg[k].first, agg[k].second);
+    out += line;
+  }
+  snprintf(buf, cap, "%s", out.c_str());
+  h->ev_used = 0;
+  h->recs.clear();
+  return CFB_OK;
+}
+
 int cfb_debug_buffer(const cfb_handle* h, int B, int T, const char* name, size_t* offset, size_t* bytes) {
   if (!h || !name || !offset || !bytes || B < 1 || T < 1) return fail(h, CFB_ERR_INVALID_ARG, "cfb_debug_buffer: bad argument");
   const Plan p = make_plan(h, B, T);
@@ -538,9 +589,32 @@ int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t
   int launches = 0;
   float* raw = v ? reinterpret_cast<float*>(ws + pl.raw) : nullptr;
 
+  // profiling: tick(label) before a launch group, tock() after it (CUDA events on the forward's stream)
+  size_t prof_e0 = 0;
+  const char* prof_label = nullptr;
+  auto tick = [&](const char* label) {
+    if (!h->profiling) return;
+    if (h->ev_used + 2 > h->ev_pool.size()) {
+      prof_label = nullptr;
+      return;
+    }
+    prof_label = label;
+    prof_e0 = h->ev_used++;
+    cudaEventRecord(h->ev_pool[prof_e0], st);
+  };
+  auto tock = [&]() {
+    if (!h->profiling || !prof_label) return;
+    const size_t e1 = h->ev_used++;
+    cudaEventRecord(h->ev_pool[e1], st);
+    h->recs.push_back({prof_label, prof_e0, e1});
+    prof_label = nullptr;
+  };
+
 #define CFB_TRY(expr, what)                                                                        \
   do {                                                                                             \
+    tick(what);                                                                                    \
     int rc_ = (expr);                                                                              \
+    tock();                                                                                        \
     if (rc_ != 0) {                                                                                \
       return fail(h, CFB_ERR_CUDA, std::string("cfb_forward: ") + what + " failed: " +             \
                                        (err.empty() ? cudaGetErrorString((cudaError_t)rc_) : err)); \

@@ -332,6 +332,23 @@ class ConformerEncoder(nn.Module):
                 ctypes.c_void_p(ws_ptr), nbytes.value, ctypes.c_void_p(stream)), self._handle, "cfb_forward")
         return encoded.transpose(1, 2), encoded_len
 
+    # profiling ---------------------------------------------------------------------------------------------------
+    def set_profiling(self, on: bool) -> None:
+        """Bracket every kernel of subsequent forwards with CUDA events (cfb_set_profiling)."""
+        if self._handle is None:
+            self.prepare()
+        _lib.check(_lib.load_library().cfb_set_profiling(self._handle, int(on)), self._handle, "cfb_set_profiling")
+
+    def profile_report(self):
+        """{label: (launches, total_ms)} for the forwards since the last report (synchronises)."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        _lib.check(_lib.load_library().cfb_profile_report(self._handle, buf, len(buf)), self._handle, "cfb_profile_report")
+        out = OrderedDict()
+        for line in buf.value.decode().splitlines():
+            label, n, ms = line.split("\t")
+            out[label] = (int(n), float(ms))
+        return out
+
     # debugging / tests -------------------------------------------------------------------------------------------
     def last_launch_count(self) -> int:
         return _lib.load_library().cfb_last_launch_count(self._handle) if self._handle else 0

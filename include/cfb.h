@@ -113,6 +113,13 @@ CFB_API int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const
  * "y1" "y2" "x" "a" "h" "qkv" "ctx" "g" "c" "pe" "pos".  Offsets are bytes from the workspace base. */
 CFB_API int cfb_debug_buffer(const cfb_handle* h, int B, int T, const char* name, size_t* offset, size_t* bytes);
 
+/* Per-kernel timing (bench.py's roofline): when on, cfb_forward brackets every launch with CUDA events on the
+ * forward's own stream (still enqueue-only).  cfb_profile_report synchronises on the recorded events, writes one
+ * line per kernel label "label<TAB>launches<TAB>total_ms\n" for everything recorded since the last report into
+ * buf (NUL-terminated, truncated to cap) and clears the records. */
+CFB_API int cfb_set_profiling(cfb_handle* h, int on);
+CFB_API int cfb_profile_report(cfb_handle* h, char* buf, size_t cap);
+
 /* Number of kernels the last cfb_forward call enqueued (for bench.py's gpu_launches). */
 CFB_API int cfb_last_launch_count(const cfb_handle* h);
 
