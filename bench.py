@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the Conformer encoder forward (BASELINE.json metric: audio-seconds per second, RTFx).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repository's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's algorithm on host cores
+
+A step = one forward pass of the encoder over one synthetic batch.  Workload at every N: BASELINE.json configs[1],
+Conformer-CTC Large encoder (d_model 512, 17 layers, 8 heads, ff x4, striding x4), batch 32 x 20 s (T = 2000 mel
+frames, full lengths) PER GPU (weak scaling, utterances are independent, no data-path collective).
+
+Printed JSON (one line, rank 0):
+  value     whole-job audio-s/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through ConformerEncoder.forward with HOST buffers: pinned H2D of the features and D2H of
+            (encoded, encoded_len) inside the timed region
+  roofline  dominant kernel family (tcgen05 GEMMs): algorithmic FLOPs / CUDA-event time, against the measured
+            sustained bf16 peak in MEASURED_PEAKS.json; `kernels` lists every kernel family the same way
+  cpu_baseline  the oracle (CPU restatement of the reference, oracle/conformer_oracle.py) timed on this box's host
+            cores on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Conformer-L encoder audio-sec/sec (RTFx)"
+UNIT = "audio-sec/sec"
+FRAME_SEC = 0.01  # 10 ms hop (configs/conformer_ctc_bpe.yaml:83)
+
+WORKLOADS = {
+    # name: (encoder kwargs, batch, frames)
+    "cfg2": (dict(feat_in=80, n_layers=17, d_model=512, n_heads=8), 32, 2000),
+    "cfg2_18l": (dict(feat_in=80, n_layers=18, d_model=512, n_heads=8), 32, 2000),
+    "cfg4": (dict(feat_in=80, n_layers=18, d_model=256, n_heads=4), 256, 400),
+    "cfg5": (dict(feat_in=80, n_layers=17, d_model=512, n_heads=8), 1, 30000),
+    "tiny": (dict(feat_in=80, n_layers=2, d_model=256, n_heads=4), 4, 400),
+}
+
+
+def workload_config(name, n_gpus):
+    kw, b, t = WORKLOADS[name]
+    return {
+        "workload": f"{name}: Conformer encoder d_model={kw['d_model']} layers={kw['n_layers']} heads={kw['n_heads']} "
+                    f"ff_x4 conv_k31 striding_x4, batch {b} x {t * FRAME_SEC:.0f} s ({t} mel frames, full lengths) per GPU",
+        "per_gpu_batch": b, "frames": t, "global_batch": b * n_gpus, "parallelism": f"dp{n_gpus} (no collective)",
+        "l2": "working set per step (>1 GB of activations) exceeds the 126 MB L2; no flush needed",
+    }
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=float(p.get("bf16_tflops_sustained", 1399.7)), gbs=float(p.get("hbm_gbs", 6454.6)),
+                    source="MEASURED_PEAKS.json (sustained bf16, copy bandwidth)")
+    return dict(tflops=1400.0, gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def build_encoder(kw, device):
+    import conformer_nemo_b200 as cn
+
+    torch.manual_seed(0)
+    enc = cn.ConformerEncoder(**kw)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():  # the defaults of these are degenerate (zeros / identity)
+        for layer in enc.layers:
+            layer.self_attn.pos_bias_u.copy_(torch.randn(layer.self_attn.pos_bias_u.shape, generator=g) * 0.1)
+            layer.self_attn.pos_bias_v.copy_(torch.randn(layer.self_attn.pos_bias_v.shape, generator=g) * 0.1)
+            bn = layer.conv.batch_norm
+            bn.running_mean.copy_(torch.randn(bn.running_mean.shape, generator=g) * 0.1)
+            bn.running_var.copy_(torch.rand(bn.running_var.shape, generator=g) * 0.5 + 0.75)
+    enc.mark_weights_dirty()
+    return enc.to(device).eval()
+
+
+def algorithmic_costs(kw, b, t):
+    """Per-forward algorithmic FLOPs (tensor-bound kernels) / bytes (memory-bound kernels), keyed by the kernel
+    labels of cfb_forward.  Formulas: SURVEY.md section 8(d); GEMM = 2*M*N*K on unpadded dims."""
+    d, L, H = kw["d_model"], kw["n_layers"], kw["n_heads"]
+    c, ff = d, 4 * d
+    t1 = (t - 1) // 2 + 1
+    t2 = (t1 - 1) // 2 + 1
+    n = b * t2
+    f1, f2 = 40, 20
+    fl = {
+        "subsample conv 2": 2 * 9 * c * c * n * f2,
+        "pre_encode.out": 2 * n * f2 * c * d,
+        "linear_pos": 2 * (2 * t2 - 1) * d * d * L,
+        "qkv projection": L * 2 * n * d * 3 * d,
+        "linear_out": L * 2 * n * d * d,
+        "pointwise_conv1+glu": L * 2 * n * d * 2 * d,
+        "pointwise_conv2": L * 2 * n * d * d,
+        "linear1+swish": 2 * L * 2 * n * d * ff,
+        "linear2": 2 * L * 2 * n * d * ff,
+        "rel-pos attention": L * 6 * b * t2 * t2 * d,
+    }
+    by = {
+        "subsample conv 0": b * 80 * t * 4 + b * t1 * f1 * c * 2,
+        "norm_feed_forward": 2 * L * n * d * 6,
+        "norm_self_att": L * n * d * 6,
+        "norm_conv": L * n * d * 6,
+        "norm_out": L * n * d * 8,
+        "depthwise conv": L * (n * d * 4 + 31 * d * 4),
+    }
+    return fl, by
+
+
+GEMM_LABELS = ["pre_encode.out", "linear_pos", "qkv projection", "linear_out", "pointwise_conv1+glu", "pointwise_conv2",
+               "linear1+swish", "linear2"]
+
+
+def run_b200(args):
+    n_gpus = args.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    kw, b, t = WORKLOADS[args.workload]
+    enc = build_encoder(kw, device)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(b, kw["feat_in"], t, generator=g).pin_memory()
+    len_host = torch.full((b,), t, dtype=torch.int64).pin_memory()
+    x_dev = x_host.to(device)
+    len_dev = len_host.to(device)
+    audio_sec = float(len_host.sum()) * FRAME_SEC
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        tt = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---------------- device-resident throughput
+    for _ in range(max(args.warmup, 3)):
+        enc(audio_signal=x_dev, length=len_dev)
+    launches_per_step = enc.last_launch_count()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        y, ylen = enc(audio_signal=x_dev, length=len_dev)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = audio_sec * world / (ms_step / 1e3)
+
+    # ---------------- end to end through the public API with host buffers
+    out_host = torch.empty(b, y.shape[2], y.shape[1], dtype=torch.float32).pin_memory()
+    olen_host = torch.empty(b, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        x_dev.copy_(x_host, non_blocking=True)
+        len_dev.copy_(len_host, non_blocking=True)
+        yy, ll = enc(audio_signal=x_dev, length=len_dev)
+        out_host.copy_(yy.transpose(1, 2), non_blocking=True)
+        olen_host.copy_(ll, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e = {"value": audio_sec * world / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": x_host.numel() * 4 + len_host.numel() * 8,
+           "d2h_bytes_per_step": out_host.numel() * 4 + olen_host.numel() * 4}
+
+    # ---------------- per-kernel timing pass (CUDA events on the forward's stream) -> roofline
+    roofline, kernels = None, None
+    if rank == 0:
+        pk = peaks()
+        enc.set_profiling(True)
+        prof_steps = 3
+        for _ in range(prof_steps):
+            enc(audio_signal=x_dev, length=len_dev)
+        rep = enc.profile_report()
+        enc.set_profiling(False)
+        fl, by = algorithmic_costs(kw, b, t)
+        kernels = {}
+        for label, (n_launch, ms) in rep.items():
+            per_fwd_ms = ms / prof_steps
+            ent = {"launches_per_step": n_launch // prof_steps, "ms_per_step": round(per_fwd_ms, 4)}
+            if label in fl:
+                ach = fl[label] / (per_fwd_ms / 1e3) / 1e12
+                ent.update(bound="tensor", achieved=round(ach, 1), unit="TFLOP/s", frac=round(ach / pk["tflops"], 4))
+            elif label in by:
+                ach = by[label] / (per_fwd_ms / 1e3) / 1e9
+                ent.update(bound="hbm", achieved=round(ach, 1), unit="GB/s", frac=round(ach / pk["gbs"], 4))
+            kernels[label] = ent
+        gemm_ms = sum(rep[l][1] for l in GEMM_LABELS if l in rep) / prof_steps
+        gemm_fl = sum(fl[l] for l in GEMM_LABELS if l in rep)
+        gemm_launches = sum(rep[l][0] for l in GEMM_LABELS if l in rep) // prof_steps
+        ach = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        roofline = {"kernel": "gemm_tc_kernel (tcgen05 GEMM family: " + ", ".join(GEMM_LABELS) + ")",
+                    "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": round(ach / pk["tflops"], 4), "traffic": None, "peak_source": pk["source"],
+                    "launches_per_step": gemm_launches, "avg_launch_ms": round(gemm_ms / max(gemm_launches, 1), 5),
+                    "share_of_step": round(gemm_ms / sum(v[1] for v in rep.values()) * prof_steps, 4),
+                    "how": f"CUDA events around every launch, {prof_steps} extra steps after the timed region"}
+
+    # ---------------- CPU baseline (oracle = CPU port of the reference algorithm), bounded sample, N=1 rank 0 only
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = time_oracle(kw, {k: v.detach().float().cpu() for k, v in enc.state_dict().items()},
+                                   sample_b=2, t=t, warmup=1, steps=2)
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic (randn log-mel features, random-init weights)",
+        "config": workload_config(args.workload, world), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "kernels": kernels,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+
+
+def time_oracle(kw, sd, sample_b, t, warmup, steps):
+    """Times the oracle on the host cores.  The only place the benchmark touches oracle/ (cpu_baseline leg)."""
+    from oracle import conformer_oracle as oc
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = oc.EncoderConfig(feat_in=kw["feat_in"], n_layers=kw["n_layers"], d_model=kw["d_model"], n_heads=kw["n_heads"])
+    if sd is None:
+        sd = oc.random_state_dict(cfg, 0)
+    sd = {k: v for k, v in sd.items() if not k.endswith("num_batches_tracked")}
+    x, length = oc.synthetic_batch(sample_b, kw["feat_in"], t, None, seed=1234)
+    for _ in range(warmup):
+        oc.encoder_forward(sd, cfg, x, length)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oc.encoder_forward(sd, cfg, x, length)
+        times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": sample_b * t * FRAME_SEC / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sec_per_step": sec,
+            "sample": f"{sample_b} of the workload's utterances x {t * FRAME_SEC:.0f} s, fp32, torch {torch.__version__} "
+                      f"CPU kernels, {cores} threads, mean of {steps} after {warmup} warm-up"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm (oracle port; the reference package itself cannot be
+    imported -- hydra / pytorch_lightning / sox are absent -- and does not travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    kw, b, t = WORKLOADS[args.workload]
+    res = time_oracle(kw, None, sample_b=2, t=t, warmup=min(args.warmup, 2), steps=max(1, min(args.steps, 10)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
+        "steps": max(1, min(args.steps, 10)), "warmup": min(args.warmup, 2), "ms_per_step": res["sec_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, world), "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
