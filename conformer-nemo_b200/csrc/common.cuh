@@ -84,5 +84,7 @@ int launch_im2col(const float* y_in, float* cols, int B, int C, int Th, int Fh, 
 // TMA descriptor encoder (cuTensorMapEncodeTiled resolved through the runtime; libcuda is not linked)
 bool encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, std::string* err);
+bool encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, std::string* err);
 
 }  // namespace cfb

@@ -82,9 +82,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------------------------------------ depth-wise conv
 // out[b,t,c] = swish(bias[c] + sum_k taps[c][k] * x[b, t + k - (K-1)/2, c]), zero outside [0,T).
-// Block: 64 channels x 64 frames of one sequence; the (64 + K - 1)-frame halo tile is staged in shared memory as
-// fp32; each thread owns a channel pair and 8 consecutive frames and slides the K-tap window over registers.
-constexpr int kDwC = 64, kDwT = 64, kDwMaxK = 31;
+// Block: 64 channels x 128 frames of one sequence.  The (128 + K - 1)-frame halo tile is staged in shared memory in
+// the activation dtype with 16-byte cp.async copies (all in flight at once); each thread owns a channel pair and 16
+// consecutive frames and slides the K-tap window over registers.  Reads and writes are 128-byte row segments.
+constexpr int kDwC = 64, kDwT = 128, kDwMaxK = 31, kDwStrip = 16;
 
 template <typename T>
 __device__ __forceinline__ float2 load2(const T* p);
@@ -105,7 +106,10 @@ template <typename T, bool kFast>
 __global__ void __launch_bounds__(256) depthwise_kernel(const T* __restrict__ x, const float* __restrict__ taps,
                                                         const float* __restrict__ bias, T* __restrict__ out, int T_len,
                                                         int d, int ksize) {
-  __shared__ __align__(16) float tile[kDwT + kDwMaxK - 1][kDwC + 2];
+  constexpr int kRows = kDwT + kDwMaxK - 1;
+  constexpr int kVec = 16 / sizeof(T);       // elements per 16-byte chunk
+  constexpr int kChunks = kDwC / kVec;       // chunks per tile row
+  __shared__ __align__(16) T tile[kRows][kDwC];
   const int half = (ksize - 1) / 2;
   const int tblocks = (T_len + kDwT - 1) / kDwT;
   const int b = blockIdx.x / tblocks;
@@ -114,48 +118,57 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const T* __restrict__ x,
   const T* xb = x + static_cast<long long>(b) * T_len * d;
   T* ob = out + static_cast<long long>(b) * T_len * d;
   const int span = kDwT + ksize - 1;
-  // stage: 32 channel pairs x span frames
-  for (int i = threadIdx.x; i < span * (kDwC / 2); i += 256) {
-    const int r = i / (kDwC / 2), cp = i % (kDwC / 2);
-    const int t = t0 - half + r, c = c0 + 2 * cp;
-    float2 v = make_float2(0.f, 0.f);
-    if (t >= 0 && t < T_len && c < d) v = load2<T>(xb + static_cast<long long>(t) * d + c);
-    tile[r][2 * cp] = v.x;
-    tile[r][2 * cp + 1] = v.y;
+  for (int i = threadIdx.x; i < span * kChunks; i += 256) {
+    const int r = i / kChunks, ch = i % kChunks;
+    const int t = t0 - half + r, c = c0 + ch * kVec;
+    T* dst = &tile[r][ch * kVec];
+    if (t >= 0 && t < T_len && c + kVec <= d) {
+      const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(xb + static_cast<long long>(t) * d + c)
+                   : "memory");
+    } else {
+#pragma unroll
+      for (int e = 0; e < kVec; ++e) {
+        const bool ok = t >= 0 && t < T_len && c + e < d;
+        dst[e] = ok ? xb[static_cast<long long>(t) * d + c + e] : static_cast<T>(0.f);
+      }
+    }
   }
-  __syncthreads();
-  const int cp = threadIdx.x & 31;  // channel pair
-  const int strip = threadIdx.x >> 5;  // 8 strips of 8 frames
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const int cp = threadIdx.x & 31;     // channel pair
+  const int strip = threadIdx.x >> 5;  // 8 strips of 16 frames
   const int c = c0 + 2 * cp;
-  if (c >= d) return;
+  const bool live = c < d;
   float w0[kDwMaxK], w1[kDwMaxK];
 #pragma unroll
   for (int k = 0; k < kDwMaxK; ++k) {
-    w0[k] = (k < ksize) ? __ldg(taps + static_cast<long long>(c) * ksize + k) : 0.f;
-    w1[k] = (k < ksize) ? __ldg(taps + static_cast<long long>(c + 1) * ksize + k) : 0.f;
+    w0[k] = (live && k < ksize) ? __ldg(taps + static_cast<long long>(c) * ksize + k) : 0.f;
+    w1[k] = (live && k < ksize) ? __ldg(taps + static_cast<long long>(c + 1) * ksize + k) : 0.f;
   }
-  float a0[8], a1[8];
-  const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
+  const float b0 = live ? __ldg(bias + c) : 0.f, b1 = live ? __ldg(bias + c + 1) : 0.f;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (!live) return;
+  float a0[kDwStrip], a1[kDwStrip];
 #pragma unroll
-  for (int o = 0; o < 8; ++o) a0[o] = b0, a1[o] = b1;
+  for (int o = 0; o < kDwStrip; ++o) a0[o] = b0, a1[o] = b1;
 #pragma unroll
-  for (int j = 0; j < 8 + kDwMaxK - 1; ++j) {
-    if (j < 8 + ksize - 1) {
-      const float2 vv = *reinterpret_cast<const float2*>(&tile[strip * 8 + j][2 * cp]);
-      const float v0 = vv.x, v1 = vv.y;
+  for (int j = 0; j < kDwStrip + kDwMaxK - 1; ++j) {
+    if (j < kDwStrip + ksize - 1) {
+      const float2 vv = load2<T>(&tile[strip * kDwStrip + j][2 * cp]);
 #pragma unroll
-      for (int o = 0; o < 8; ++o) {
+      for (int o = 0; o < kDwStrip; ++o) {
         const int k = j - o;
         if (k >= 0 && k < kDwMaxK) {
-          a0[o] = fmaf(w0[k], v0, a0[o]);
-          a1[o] = fmaf(w1[k], v1, a1[o]);
+          a0[o] = fmaf(w0[k], vv.x, a0[o]);
+          a1[o] = fmaf(w1[k], vv.y, a1[o]);
         }
       }
     }
   }
 #pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    const int t = t0 + strip * 8 + o;
+  for (int o = 0; o < kDwStrip; ++o) {
+    const int t = t0 + strip * kDwStrip + o;
     if (t < T_len) {
       float s0, s1;
       if constexpr (kFast) {
@@ -205,14 +218,17 @@ __global__ void pos_table_kernel(TOut* __restrict__ out, const float* __restrict
 // y1[b, t1, f1, c] = relu(bias[c] + sum_{kh,kw} w[c][kh][kw] * x[b][2 f1 + kw - 1][2 t1 + kh - 1])   (x is (B,F,T))
 // written in the parity-split channels-last layout [B][plane = (t1&1)*2 + (f1&1)][Th][Fh][C] that lets the second
 // convolution fetch each filter tap as one dense TMA box.  Positions with t1 >= T1 or f1 >= F1 are written as 0.
+// Output-write bound (it is the largest tensor of the network): each thread keeps the 9 taps + bias of 8 channels in
+// registers and walks over output positions; a warp's 16-byte stores cover 512 contiguous bytes.
 constexpr int kS1T = 16;  // t1 rows per block
 
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) subsample_first_kernel(const TIn* __restrict__ feats,
                                                               const float* __restrict__ w9,
                                                               const float* __restrict__ bias, TOut* __restrict__ y,
-                                                              int F, int T, int C, int T1, int F1, int Th, int Fh) {
-  extern __shared__ float patch[];  // [F + 2][2*kS1T + 1 (+1 pad)]  frames 2*t1_0 - 1 .. 2*(t1_0 + kS1T - 1) + 1
+                                                              int F, int T, int C, int T1, int F1, int Th, int Fh,
+                                                              int groups_per_block) {
+  extern __shared__ float patch[];  // [F + 2][2*kS1T + 2]: frames 2*t1_0 - 1 .. 2*(t1_0 + kS1T - 1) + 1
   const int pw = 2 * kS1T + 2;
   const int tblocks = (2 * Th + kS1T - 1) / kS1T;
   const int b = blockIdx.x / tblocks;
@@ -226,18 +242,26 @@ __global__ void __launch_bounds__(256) subsample_first_kernel(const TIn* __restr
     patch[fr * pw + tc] = v;
   }
   __syncthreads();
-  const int groups = C / 8;  // 8 channels per thread
+  const int g_local = threadIdx.x % groups_per_block;
+  const int lane_pos = threadIdx.x / groups_per_block;
+  const int n_pos_lanes = 256 / groups_per_block;
+  const int g = blockIdx.y * groups_per_block + g_local;  // 8 channels per group
+  if (g * 8 >= C || lane_pos >= n_pos_lanes) return;
+  float w[8][9], bs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    bs[j] = __ldg(bias + g * 8 + j);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) w[j][q] = __ldg(w9 + (g * 8 + j) * 9 + q);
+  }
   const int positions = kS1T * 2 * Fh;
-  for (int item = threadIdx.x; item < positions * groups; item += 256) {
-    const int g = item % groups;
-    const int pos = item / groups;
+  for (int pos = lane_pos; pos < positions; pos += n_pos_lanes) {
     const int f1 = pos % (2 * Fh);
     const int tt = pos / (2 * Fh);
     const int t1 = t1_0 + tt;
-    if (t1 >= 2 * Th) continue;
+    if (t1 >= 2 * Th) break;
     float acc[8];
-    const bool live = (t1 < T1) && (f1 < F1);
-    if (live) {
+    if ((t1 < T1) && (f1 < F1)) {
       float in[9];
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh)
@@ -245,10 +269,9 @@ __global__ void __launch_bounds__(256) subsample_first_kernel(const TIn* __restr
         for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = patch[(2 * f1 + kw) * pw + (2 * tt + kh)];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int c = g * 8 + j;
-        float a = __ldg(bias + c);
+        float a = bs[j];
 #pragma unroll
-        for (int q = 0; q < 9; ++q) a = fmaf(__ldg(w9 + c * 9 + q), in[q], a);
+        for (int q = 0; q < 9; ++q) a = fmaf(w[j][q], in[q], a);
         acc[j] = fmaxf(a, 0.f);
       }
     } else {
@@ -339,10 +362,13 @@ int launch_subsample_first(const void* feats, bool feats_bf16, const float* w9, 
   if (C % 8 != 0) return -1;
   const int tblocks = (2 * Th + kS1T - 1) / kS1T;
   const size_t smem = static_cast<size_t>(F + 2) * (2 * kS1T + 2) * sizeof(float);
-  const int grid = B * tblocks;
+  const int groups = C / 8;
+  const int gpb = groups < 64 ? groups : 64;  // channel groups per block; the other threads walk positions
+  const dim3 grid(B * tblocks, (groups + gpb - 1) / gpb);
 #define CFB_S1(TIN, TOUT)                                                                                         \
   subsample_first_kernel<TIN, TOUT><<<grid, 256, smem, st>>>(reinterpret_cast<const TIN*>(feats), w9, bias,       \
-                                                             reinterpret_cast<TOUT*>(y_out), F, T, C, T1, F1, Th, Fh)
+                                                             reinterpret_cast<TOUT*>(y_out), F, T, C, T1, F1, Th, \
+                                                             Fh, gpb)
   if (feats_bf16) {
     if (out_bf16)
       CFB_S1(bf16, bf16);

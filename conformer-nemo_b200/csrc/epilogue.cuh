@@ -83,23 +83,27 @@ __device__ __forceinline__ void load_bias32(const float* bias, int col0, int n, 
   }
 }
 
-// acc: 32 accumulator columns [col0, col0+32) of logical row `row` (0 <= row < p.M, checked by the caller);
-// out_row: the row of the output matrix it maps to (differs from `row` only for the implicit-GEMM convolution).
-template <int EPI, typename TOut>
-__device__ __forceinline__ void epi_apply(const EpiParams& p, long long out_row, int col0, float (&acc)[32]) {
-  constexpr bool kFast = OutTraits<TOut>::kFast;
+// Arithmetic part of the epilogue.  acc: 32 accumulator columns [col0, col0+32) of the output row `out_row`
+// (masking uses out_row / frames_per_seq).  On return acc holds the values to store:
+//   LINEAR / SWISH / RELU : 32 values for output columns col0..          (zeroed at padded frames when p.lens is set)
+//   RESID                 : 32 increments alpha * (acc + bias) to be ADDED to the fp32 residual stream
+//   QKV                   : pass 0 -> acc + bias (q+u | k | v), pass 1 -> acc + bias2 (q+v; only for col0 < qkv_dp)
+//   GLU                   : 16 values a * sigmoid(g) for output columns col0/2.. (zeroed at padded frames)
+template <int EPI, bool kFast>
+__device__ __forceinline__ void epi_compute(const EpiParams& p, long long out_row, int col0, float (&acc)[32],
+                                            int pass) {
   const int n = min(32, p.N - col0);
-  if (n <= 0) return;
   float b[32];
-  load_bias32(p.bias, col0, n, b);
-
-  if constexpr (EPI == EPI_LINEAR || EPI == EPI_SWISH || EPI == EPI_RELU) {
-    bool keep = true;
+  load_bias32((EPI == EPI_QKV && pass == 1) ? p.bias2 : p.bias, col0, n, b);
+  bool keep = true;
+  if constexpr (EPI == EPI_LINEAR || EPI == EPI_SWISH || EPI == EPI_RELU || EPI == EPI_GLU) {
     if (p.lens != nullptr) {
       const int seq = static_cast<int>(out_row / p.frames_per_seq);
       const int t = static_cast<int>(out_row - static_cast<long long>(seq) * p.frames_per_seq);
       keep = t < p.lens[seq];
     }
+  }
+  if constexpr (EPI == EPI_LINEAR || EPI == EPI_SWISH || EPI == EPI_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float x = acc[j] + b[j];
@@ -107,56 +111,52 @@ __device__ __forceinline__ void epi_apply(const EpiParams& p, long long out_row,
       if constexpr (EPI == EPI_RELU) x = fmaxf(x, 0.f);
       acc[j] = keep ? x : 0.f;
     }
-    store_cols(reinterpret_cast<TOut*>(p.out) + out_row * p.ldo + col0, acc, n);
   } else if constexpr (EPI == EPI_RESID) {
-    float* r = reinterpret_cast<float*>(p.out) + out_row * p.ldo + col0;
-    if (n == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 t = *reinterpret_cast<const float4*>(r + j);
-        t.x += p.alpha * (acc[j] + b[j]);
-        t.y += p.alpha * (acc[j + 1] + b[j + 1]);
-        t.z += p.alpha * (acc[j + 2] + b[j + 2]);
-        t.w += p.alpha * (acc[j + 3] + b[j + 3]);
-        *reinterpret_cast<float4*>(r + j) = t;
-      }
-    } else {
-      for (int j = 0; j < n; ++j) r[j] += p.alpha * (acc[j] + b[j]);
-    }
+    for (int j = 0; j < 32; ++j) acc[j] = p.alpha * (acc[j] + b[j]);
   } else if constexpr (EPI == EPI_QKV) {
-    // accumulator columns: [0,Dp) q, [Dp,2Dp) k, [2Dp,3Dp) v ; output columns: [q+u | q+v | k | v]
-    TOut* o = reinterpret_cast<TOut*>(p.out) + out_row * p.ldo;
-    if (col0 < p.qkv_dp) {
-      float b2[32], v2[32];
-      load_bias32(p.bias2, col0, n, b2);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v2[j] = acc[j] + b2[j];
-        acc[j] = acc[j] + b[j];
-      }
-      store_cols(o + col0, acc, n);
-      store_cols(o + p.qkv_dp + col0, v2, n);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = acc[j] + b[j];
-      store_cols(o + p.qkv_dp + col0, acc, n);
-    }
+    for (int j = 0; j < 32; ++j) acc[j] = acc[j] + b[j];
   } else if constexpr (EPI == EPI_GLU) {
-    // accumulator columns come in groups of 32 = [16 'a' channels | the matching 16 gate channels]
-    bool keep = true;
-    if (p.lens != nullptr) {
-      const int seq = static_cast<int>(out_row / p.frames_per_seq);
-      const int t = static_cast<int>(out_row - static_cast<long long>(seq) * p.frames_per_seq);
-      keep = t < p.lens[seq];
-    }
-    float o[32];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float a = acc[j] + b[j];
       const float g = acc[16 + j] + b[16 + j];
-      o[j] = keep ? a * sigmoidf_<kFast>(g) : 0.f;
+      acc[j] = keep ? a * sigmoidf_<kFast>(g) : 0.f;
     }
-    store_cols(reinterpret_cast<TOut*>(p.out) + out_row * p.ldo + (col0 >> 1), o, 16);
+  }
+}
+
+// Direct-to-global form used by the validation path's stand-alone epilogue kernel.
+template <int EPI, typename TOut>
+__device__ __forceinline__ void epi_apply(const EpiParams& p, long long out_row, int col0, float (&acc)[32]) {
+  constexpr bool kFast = OutTraits<TOut>::kFast;
+  const int n = min(32, p.N - col0);
+  if (n <= 0) return;
+  if constexpr (EPI == EPI_RESID) {
+    epi_compute<EPI, kFast>(p, out_row, col0, acc, 0);
+    float* r = reinterpret_cast<float*>(p.out) + out_row * p.ldo + col0;
+    for (int j = 0; j < n; ++j) r[j] += acc[j];
+  } else if constexpr (EPI == EPI_QKV) {
+    TOut* o = reinterpret_cast<TOut*>(p.out) + out_row * p.ldo;
+    if (col0 < p.qkv_dp) {
+      float v2[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v2[j] = acc[j];
+      epi_compute<EPI, kFast>(p, out_row, col0, acc, 0);
+      epi_compute<EPI, kFast>(p, out_row, col0, v2, 1);
+      store_cols(o + col0, acc, n);
+      store_cols(o + p.qkv_dp + col0, v2, n);
+    } else {
+      epi_compute<EPI, kFast>(p, out_row, col0, acc, 0);
+      store_cols(o + p.qkv_dp + col0, acc, n);
+    }
+  } else if constexpr (EPI == EPI_GLU) {
+    epi_compute<EPI, kFast>(p, out_row, col0, acc, 0);
+    store_cols(reinterpret_cast<TOut*>(p.out) + out_row * p.ldo + (col0 >> 1), acc, 16);
+  } else {
+    epi_compute<EPI, kFast>(p, out_row, col0, acc, 0);
+    store_cols(reinterpret_cast<TOut*>(p.out) + out_row * p.ldo + col0, acc, n);
   }
 }
 

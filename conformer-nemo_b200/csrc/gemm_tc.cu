@@ -4,9 +4,12 @@
 // One persistent CTA per SM, 192 threads, warp-specialised:
 //   warp 0      TMA producer (one lane): A and W tiles, 128-byte swizzle, STAGES-deep mbarrier ring
 //   warp 1      MMA issuer (one lane): tcgen05.mma cta_group::1, 128 x BN x 16 per instruction, BLOCK_K = 64
-//   warps 2..5  epilogue: tcgen05.ld 32x32b (thread = output row), bias / activation / residual, 16-byte stores
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (thread = output row), bias / activation / mask in registers, values
+//               staged into a 128-byte-swizzled smem box per warp (32 rows x 128 B, double-buffered) and written
+//               with TMA stores -- plain stores for bf16 / fp32 outputs, cp.reduce.async.bulk (.add.f32) into the
+//               fp32 residual stream -- so every global write is a full 128-byte line
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop
-// of tile i+1.  M/N/K tails are handled by TMA zero fill on the load side and predication on the store side.
+// of tile i+1.  M/N/K tails are handled by TMA zero fill on the load side and TMA clipping on the store side.
 #include <stdio.h>
 
 #include "common.cuh"
@@ -39,13 +42,16 @@ struct SmemLayout {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kStagingOffset = STAGES * kStageBytes;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+  static constexpr int kStagingBytes = 4 * 2 * 4096;
+  static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
 template <int BN, int STAGES, int EPI, typename TOut, bool CONV>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const TcParams p) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -63,6 +69,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       ptx::prefetch_tmap(&tmA);
       ptx::prefetch_tmap(&tmB);
+      ptx::prefetch_tmap(&tmO);
       for (int s = 0; s < STAGES; ++s) {
         ptx::mbar_init(&full_bar[s], 1);
         ptx::mbar_init(&empty_bar[s], 1);
@@ -152,8 +159,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
+    constexpr bool kFast = OutTraits<TOut>::kFast;
+    constexpr int kBoxCols = 128 / static_cast<int>(sizeof(TOut));           // output columns per 128-byte box row
+    constexpr int kAccPerBox = (EPI == EPI_GLU) ? 2 * kBoxCols : kBoxCols;   // accumulator columns feeding one box
+    constexpr int kChunks = kAccPerBox / 32;
+    constexpr int kBoxes = BN / kAccPerBox;
+    static_assert(kBoxes >= 1, "tile narrower than one output box");
     const int quarter = warp & 3;  // TMEM lanes this warp may read: [32*quarter, +32)
     const int row_in_tile = quarter * 32 + lane;
+    uint8_t* stage_base = smem + L::kStagingOffset + quarter * 8192;
+    const uint32_t swz = static_cast<uint32_t>(lane & 7);
+    uint32_t box_counter = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -161,14 +177,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_blk = tile / p.num_n_tiles;
       long long out_row;
       bool row_ok;
+      int cv_f0 = 0, cv_t0 = 0, cv_b = 0;
       if constexpr (CONV) {
         const int fb = m_blk % p.conv_fblocks;
         const int tb = (m_blk / p.conv_fblocks) % p.conv_tblocks;
-        const int b = m_blk / (p.conv_fblocks * p.conv_tblocks);
+        cv_b = m_blk / (p.conv_fblocks * p.conv_tblocks);
         const int t = tb * 32 + (row_in_tile >> 2);
         const int f = fb * 4 + (row_in_tile & 3);
+        cv_f0 = fb * 4;
+        cv_t0 = tb * 32 + quarter * 8;
         row_ok = (t < p.conv_To) && (f < p.conv_Fo);
-        out_row = (static_cast<long long>(b) * p.conv_To + t) * p.conv_Fo + f;
+        out_row = (static_cast<long long>(cv_b) * p.conv_To + t) * p.conv_Fo + f;
       } else {
         out_row = static_cast<long long>(m_blk) * kBlockM + row_in_tile;
         row_ok = out_row < p.ep.M;
@@ -177,21 +196,70 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_x32(t_addr + c * 32, v);
-        ptx::tc_wait_ld();
-        const int col0 = n_blk * BN + c * 32;
-        if (row_ok && col0 < p.ep.N) {
-          float acc[32];
+      for (int box = 0; box < kBoxes; ++box) {
+        const int acc_col0 = n_blk * BN + box * kAccPerBox;
+        if (acc_col0 >= p.ep.N) break;  // warp-uniform: nothing of this box is inside the matrix
+        const int n_pass = (EPI == EPI_QKV && acc_col0 < p.ep.qkv_dp) ? 2 : 1;
+#pragma unroll 1
+        for (int pass = 0; pass < n_pass; ++pass) {
+          uint8_t* sbuf = stage_base + (box_counter & 1u) * 4096;
+          if (lane == 0) ptx::bulk_wait_read<1>();  // the store that last read this buffer has drained it
+          __syncwarp();
+          uint8_t* srow = sbuf + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-          epi_apply<EPI, TOut>(p.ep, out_row, col0, acc);
+          for (int ch = 0; ch < kChunks; ++ch) {
+            uint32_t v[32];
+            ptx::tmem_ld_x32(t_addr + box * kAccPerBox + ch * 32, v);
+            ptx::tc_wait_ld();
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+            if (row_ok) epi_compute<EPI, kFast>(p.ep, out_row, acc_col0 + ch * 32, acc, pass);
+            if constexpr (sizeof(TOut) == 4) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(srow + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
+                    make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            } else {
+              constexpr int kPieces = (EPI == EPI_GLU) ? 2 : 4;  // 16-byte pieces produced by this chunk
+#pragma unroll
+              for (int j = 0; j < kPieces; ++j) {
+                uint4 u;
+                u.x = ptx::pack_bf16x2(acc[8 * j + 0], acc[8 * j + 1]);
+                u.y = ptx::pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
+                u.z = ptx::pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]);
+                u.w = ptx::pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
+                *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(ch * kPieces + j) ^ swz) << 4)) = u;
+              }
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CONV) {
+              ptx::tma_store_4d(&tmO, sbuf, acc_col0, cv_f0, cv_t0, cv_b);
+            } else {
+              const int row0 = m_blk * kBlockM + quarter * 32;
+              if constexpr (EPI == EPI_RESID) {
+                ptx::tma_reduce_add_2d(&tmO, sbuf, acc_col0, row0);
+              } else if constexpr (EPI == EPI_QKV) {
+                const int oc = (pass == 1 || acc_col0 >= p.ep.qkv_dp) ? acc_col0 + p.ep.qkv_dp : acc_col0;
+                ptx::tma_store_2d(&tmO, sbuf, oc, row0);
+              } else if constexpr (EPI == EPI_GLU) {
+                ptx::tma_store_2d(&tmO, sbuf, acc_col0 >> 1, row0);
+              } else {
+                ptx::tma_store_2d(&tmO, sbuf, acc_col0, row0);
+              }
+            }
+            ptx::bulk_commit();
+          }
+          ++box_counter;
         }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc_empty[buf]);
     }
+    if (lane == 0) ptx::bulk_wait<0>();  // all output writes complete before the CTA retires
   }
 
   ptx::tc_fence_before();
@@ -214,8 +282,8 @@ int num_sms() {
 }
 
 template <int BN, int STAGES, int EPI, typename TOut, bool CONV>
-int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t st,
-                    std::string* err) {
+int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const TcParams& p,
+                    cudaStream_t st, std::string* err) {
   using L = SmemLayout<BN, STAGES>;
   auto kern = gemm_tc_kernel<BN, STAGES, EPI, TOut, CONV>;
   static bool configured[64] = {};  // per instantiation and device
@@ -230,7 +298,7 @@ int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPara
     configured[dev & 63] = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  kern<<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, p);
+  kern<<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, tmO, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("gemm_tc launch: ") + cudaGetErrorString(e);
@@ -240,25 +308,25 @@ int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPara
 }
 
 template <int BN, int STAGES, bool CONV>
-int dispatch_epi(int epi, bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p,
-                 cudaStream_t st, std::string* err) {
+int dispatch_epi(int epi, bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                 const TcParams& p, cudaStream_t st, std::string* err) {
   if constexpr (CONV) {
-    return launch_instance<BN, STAGES, EPI_RELU, bf16, true>(tmA, tmB, p, st, err);
+    return launch_instance<BN, STAGES, EPI_RELU, bf16, true>(tmA, tmB, tmO, p, st, err);
   } else {
     switch (epi) {
       case EPI_LINEAR:
-        return out_bf16 ? launch_instance<BN, STAGES, EPI_LINEAR, bf16, false>(tmA, tmB, p, st, err)
-                        : launch_instance<BN, STAGES, EPI_LINEAR, float, false>(tmA, tmB, p, st, err);
+        return out_bf16 ? launch_instance<BN, STAGES, EPI_LINEAR, bf16, false>(tmA, tmB, tmO, p, st, err)
+                        : launch_instance<BN, STAGES, EPI_LINEAR, float, false>(tmA, tmB, tmO, p, st, err);
       case EPI_SWISH:
-        return launch_instance<BN, STAGES, EPI_SWISH, bf16, false>(tmA, tmB, p, st, err);
+        return launch_instance<BN, STAGES, EPI_SWISH, bf16, false>(tmA, tmB, tmO, p, st, err);
       case EPI_RELU:
-        return launch_instance<BN, STAGES, EPI_RELU, bf16, false>(tmA, tmB, p, st, err);
+        return launch_instance<BN, STAGES, EPI_RELU, bf16, false>(tmA, tmB, tmO, p, st, err);
       case EPI_RESID:
-        return launch_instance<BN, STAGES, EPI_RESID, float, false>(tmA, tmB, p, st, err);
+        return launch_instance<BN, STAGES, EPI_RESID, float, false>(tmA, tmB, tmO, p, st, err);
       case EPI_QKV:
-        return launch_instance<BN, STAGES, EPI_QKV, bf16, false>(tmA, tmB, p, st, err);
+        return launch_instance<BN, STAGES, EPI_QKV, bf16, false>(tmA, tmB, tmO, p, st, err);
       case EPI_GLU:
-        return launch_instance<BN, STAGES, EPI_GLU, bf16, false>(tmA, tmB, p, st, err);
+        return launch_instance<BN, STAGES, EPI_GLU, bf16, false>(tmA, tmB, tmO, p, st, err);
       default:
         if (err) *err = "gemm_tc: unknown epilogue";
         return -1;
@@ -300,8 +368,24 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
   p.ep = g.ep;
   p.ep.M = g.M;
   p.ep.N = g.N;
-  if (bn == 256) return dispatch_epi<256, 4, false>(g.epi, g.out_bf16, tmA, tmB, p, st, err);
-  return dispatch_epi<128, 6, false>(g.epi, g.out_bf16, tmA, tmB, p, st, err);
+  // output map: 32-row boxes, 128 bytes wide (one epilogue warp's slab)
+  CUtensorMap tmO;
+  {
+    const bool f32 = !g.out_bf16 || g.epi == EPI_RESID;
+    uint64_t cols = static_cast<uint64_t>(g.N);
+    if (g.epi == EPI_QKV) cols = static_cast<uint64_t>(g.N) + g.ep.qkv_dp;  // [q+u | q+v | k | v]
+    if (g.epi == EPI_GLU) cols = static_cast<uint64_t>(g.N) / 2;
+    if ((g.ep.ldo * (f32 ? 4 : 2)) % 16) {
+      if (err) *err = "gemm_tc: output leading dimension must be a multiple of 16 bytes";
+      return -1;
+    }
+    uint64_t dims[2] = {cols, static_cast<uint64_t>(g.M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(g.ep.ldo) * (f32 ? 4 : 2)};
+    uint32_t box[2] = {f32 ? 32u : 64u, 32u};
+    if (!encode_tmap(&tmO, g.ep.out, f32, 2, dims, strides, box, err)) return -1;
+  }
+  if (bn == 256) return dispatch_epi<256, 4, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
+  return dispatch_epi<128, 5, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
 }
 
 int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err) {
@@ -342,7 +426,17 @@ int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err) {
   p.ep.ldo = c.C_out;
   p.ep.M = c.B * c.To * c.Fo;
   p.ep.N = c.C_out;
-  return dispatch_epi<128, 6, true>(EPI_RELU, true, tmA, tmB, p, st, err);
+  CUtensorMap tmO;
+  {
+    // y2 [B][To][Fo][C]: a warp's 32 accumulator rows are 8 frames x 4 bins -> one 4-D box
+    uint64_t dims[4] = {static_cast<uint64_t>(c.C_out), static_cast<uint64_t>(c.Fo), static_cast<uint64_t>(c.To),
+                        static_cast<uint64_t>(c.B)};
+    uint64_t s1 = static_cast<uint64_t>(c.C_out) * 2;
+    uint64_t strides[3] = {s1, s1 * c.Fo, s1 * c.Fo * c.To};
+    uint32_t box[4] = {64, 4, 8, 1};
+    if (!encode_tmap_bf16(&tmO, c.y_out, 4, dims, strides, box, err)) return -1;
+  }
+  return dispatch_epi<128, 5, true>(EPI_RELU, true, tmA, tmB, tmO, p, st, err);
 }
 
 }  // namespace cfb

@@ -23,6 +23,11 @@ void resolve() {
 
 bool encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, std::string* err) {
+  return encode_tmap(map, base, false, rank, dims, strides_bytes, box, err);
+}
+
+bool encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, std::string* err) {
   std::call_once(g_once, resolve);
   if (g_encode == nullptr) {
     if (err) *err = "cuTensorMapEncodeTiled is not available (no CUDA driver?)";
@@ -38,7 +43,7 @@ bool encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64
     estr[i] = 1;
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+  CUresult r = g_encode(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                         gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
