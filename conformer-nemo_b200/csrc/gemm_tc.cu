@@ -1,10 +1,10 @@
 // tcgen05 GEMM for sm_100a:  D (M x N) = A (M x K, bf16) * W^T (W: N x K, bf16), fp32 accumulation in TMEM,
 // fused epilogue (epilogue.cuh).  Also the implicit-GEMM form of the strided 3x3 subsampling convolution.
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 320 threads, warp-specialised:
 //   warp 0      TMA producer (one lane): A and W tiles, 128-byte swizzle, STAGES-deep mbarrier ring
 //   warp 1      MMA issuer (one lane): tcgen05.mma cta_group::1, 128 x BN x 16 per instruction, BLOCK_K = 64
-//   warps 2..5  epilogue: tcgen05.ld 32x32b (thread = output row), bias / activation / mask in registers, values
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, alternating output boxes): tcgen05.ld 32x32b (thread = output row), bias / activation / mask in registers, values
 //               staged into a 128-byte-swizzled smem box per warp (32 rows x 128 B, double-buffered) and written
 //               with TMA stores -- plain stores for bf16 / fp32 outputs, cp.reduce.async.bulk (.add.f32) into the
 //               fp32 residual stream -- so every global write is a full 128-byte line
@@ -22,7 +22,8 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;  // two per TMEM lane quarter
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 struct TcParams {
   int num_tiles;
@@ -42,8 +43,8 @@ struct SmemLayout {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingOffset = STAGES * kStageBytes;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
-  static constexpr int kStagingBytes = 4 * 2 * 4096;
+  static constexpr int kStagingOffset = STAGES * kStageBytes;  // per epilogue warp: 2 buffers x (32 rows x 128 B)
+  static constexpr int kStagingBytes = kEpiWarps * 2 * 4096;
   static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
@@ -76,7 +77,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int b = 0; b < 2; ++b) {
         ptx::mbar_init(&acc_full[b], 1);
-        ptx::mbar_init(&acc_empty[b], 128);
+        ptx::mbar_init(&acc_empty[b], 32 * kEpiWarps);
       }
       ptx::fence_mbar_init();
     }
@@ -165,9 +166,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int kChunks = kAccPerBox / 32;
     constexpr int kBoxes = BN / kAccPerBox;
     static_assert(kBoxes >= 1, "tile narrower than one output box");
-    const int quarter = warp & 3;  // TMEM lanes this warp may read: [32*quarter, +32)
+    const int quarter = warp & 3;        // TMEM lanes this warp may read: [32*quarter, +32)
+    const int half = (warp - 2) >> 2;    // which of the quarter's two warps: takes boxes half, half+2, ...
     const int row_in_tile = quarter * 32 + lane;
-    uint8_t* stage_base = smem + L::kStagingOffset + quarter * 8192;
+    uint8_t* stage_base = smem + L::kStagingOffset + (warp - 2) * 8192;
     const uint32_t swz = static_cast<uint32_t>(lane & 7);
     uint32_t box_counter = 0;
     int it = 0;
@@ -196,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN;
 #pragma unroll 1
-      for (int box = 0; box < kBoxes; ++box) {
+      for (int box = half; box < kBoxes; box += kEpiWarps / 4) {
         const int acc_col0 = n_blk * BN + box * kAccPerBox;
         if (acc_col0 >= p.ep.N) break;  // warp-uniform: nothing of this box is inside the matrix
         const int n_pass = (EPI == EPI_QKV && acc_col0 < p.ep.qkv_dp) ? 2 : 1;
@@ -344,8 +346,9 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
   }
   // tile width: 256 for wide outputs when it does not hurt the wave count, else 128
   const int m_tiles = (g.M + kBlockM - 1) / kBlockM;
+  // 256-wide tiles halve the re-reads of A (the kernel is bound by L2->SM bandwidth, not by the tensor pipe)
   int bn = 128;
-  if (g.N >= 1024 && g.N % 256 == 0 && g.epi != EPI_GLU && g.epi != EPI_QKV) bn = 256;
+  if (g.N % 256 == 0) bn = 256;
   const int n_tiles = (g.N + bn - 1) / bn;
 
   CUtensorMap tmA, tmB;
@@ -384,7 +387,7 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
     uint32_t box[2] = {f32 ? 32u : 64u, 32u};
     if (!encode_tmap(&tmO, g.ep.out, f32, 2, dims, strides, box, err)) return -1;
   }
-  if (bn == 256) return dispatch_epi<256, 4, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
+  if (bn == 256) return dispatch_epi<256, 3, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
   return dispatch_epi<128, 5, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
 }
 
@@ -404,7 +407,7 @@ int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err) {
     if (!encode_tmap_bf16(&tmA, c.y_in, 5, dims, strides, box, err)) return -1;
   }
   const int K = 9 * c.C_in;
-  const int bn = 128;
+  const int bn = (c.C_out % 256 == 0) ? 256 : 128;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(c.C_out)};
     uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
@@ -436,6 +439,7 @@ int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err) {
     uint32_t box[4] = {64, 4, 8, 1};
     if (!encode_tmap_bf16(&tmO, c.y_out, 4, dims, strides, box, err)) return -1;
   }
+  if (bn == 256) return dispatch_epi<256, 3, true>(EPI_RELU, true, tmA, tmB, tmO, p, st, err);
   return dispatch_epi<128, 5, true>(EPI_RELU, true, tmA, tmB, tmO, p, st, err);
 }
 
