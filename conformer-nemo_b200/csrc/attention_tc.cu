@@ -2,15 +2,19 @@
 //
 //   ctx[i,:] = softmax_j( ((q_i+u).k_j + (q_i+v).p_{T-1+j-i}) / sqrt(dk) ) v_j        (multi_head_attention.py:195-210)
 //
-// One CTA per (128-query tile, head, sequence); 192 threads:
-//   warp 0      TMA producer: Q+u, Q+v once; per 64-key tile K, V and the 192-row band of linear_pos(pos_emb) that
-//               the tile can touch (rows T-1+j0-i0-127 .. +191), 2-stage mbarrier ring
-//   warp 1      MMA issuer (tcgen05, cta_group::1): S = (Q+u) K^T (128x64) and G = (Q+v) Pband^T (128x192) into one
-//               of two TMEM buffers, later O_part = P V (128x64) into the S columns of the same buffer
-//   warps 2..5  softmax, one query row per thread: rel_shift is an index remap -- row ii needs G[ii][127-ii+jj] --
-//               done as a warp-uniform TMEM column offset plus a 5-stage register barrel shift by (31 - lane);
-//               online softmax in fp32 (exp2), probabilities written as bf16 into a 128-byte-swizzled smem tile for
-//               the PV MMA, running output kept in registers.
+// One CTA per (128-query tile, head, sequence); 384 threads = 3 warpgroups (registers re-balanced with setmaxnreg):
+//   warp 0      TMA producer: Q+u, Q+v once; per 64-key tile K and V (3-stage ring) and the 64 NEW rows of the
+//               192-row band of linear_pos(pos_emb) the tile can touch (rows T-1+j0-i0-127 .. +191): consecutive key
+//               tiles share two thirds of their band, so the band lives in a 5-block ring of 64-row blocks
+//   warp 1      MMA issuer (tcgen05, cta_group::1): S = (Q+u) K^T (128x64) and G = (Q+v) Pband^T (128x192) into the
+//               TMEM buffer of the tile's set, later O_part = P V (128x64) into the S columns of the same buffer
+//   warps 4..11 two softmax sets of four warps (one query row per thread).  Set s owns key tiles s, s+2, ... with its
+//               own TMEM buffer, probability tile and running (max, sum, O); the sets ping-pong so one set's exp /
+//               shift work overlaps the other's MMAs, and are merged (log-sum-exp) at the end.
+//               rel_shift is an index remap -- row ii needs G[ii][127-ii+jj] -- done as a warp-uniform TMEM column
+//               offset plus a per-lane offset applied through a private shared-memory row (16-byte stores, 4-byte
+//               loads, conflict-free pitch); online softmax in fp32 (exp2); probabilities written as bf16 into a
+//               128-byte-swizzled smem tile for the PV MMA.
 // Keys j >= len[b] are masked to -inf (the reference's -10000 underflows to exactly 0 for valid rows); query rows
 // i >= len[b] are written as zeros (multi_head_attention.py:104-113).
 #include <math.h>
@@ -26,23 +30,29 @@ constexpr int kBM = 128;   // queries per CTA
 constexpr int kBN = 64;    // keys per tile
 constexpr int kDK = 64;    // padded head dim
 constexpr int kBand = 192; // >= kBM + kBN - 1, multiple of 64
-constexpr int kThreads = 192;
+constexpr int kThreads = 384;  // warpgroup 0: TMA + MMA (+2 idle warps); warpgroups 1, 2: softmax sets 0, 1
 constexpr int kQBytes = kBM * kDK * 2;     // 16 KB each for Q+u, Q+v
 constexpr int kKBytes = kBN * kDK * 2;     // 8 KB
 constexpr int kBandBytes = kBand * kDK * 2;  // 24 KB
-constexpr int kStageBytes = 2 * kKBytes + kBandBytes;  // K, V, band = 40 KB
-constexpr int kPBytes = kBM * kBN * 2;     // 16 KB probabilities
-constexpr int kOffStage = 2 * kQBytes;
-constexpr int kOffP = kOffStage + 2 * kStageBytes;
-constexpr int kOffBar = kOffP + kPBytes;
+constexpr int kKVStages = 3;               // K + V tiles, 16 KB per stage
+constexpr int kKVBytes = 2 * kKBytes;
+constexpr int kBandBlocks = 5;             // ring of 64-row band blocks (8 KB each); a tile reads 3 consecutive ones
+constexpr int kBlockBytes = 64 * kDK * 2;
+constexpr int kPBytes = kBM * kBN * 2;     // 16 KB probabilities per set
+constexpr int kShiftPitch = 68;            // words per private shift row: 63-column window + pad; == 4 (mod 32), even
+constexpr int kShiftBytes = 32 * kShiftPitch * 4;  // per softmax warp
+constexpr int kOffKV = 2 * kQBytes;
+constexpr int kOffBand = kOffKV + kKVStages * kKVBytes;
+constexpr int kOffP = kOffBand + kBandBlocks * kBlockBytes;
+constexpr int kOffShift = kOffP + 2 * kPBytes;
+constexpr int kOffBar = kOffShift + 8 * kShiftBytes;
 constexpr int kSmemTotal = kOffBar + 256 + 1024;
-constexpr uint32_t kTmemCols = 512;  // two buffers of [S 64 | G 192]
+constexpr uint32_t kTmemCols = 512;  // two buffers (one per set) of [S 64 | G 192]
 
 struct AttnParams {
   const int32_t* lens;
   bf16* ctx;
   int T, Dp;
-  int pos_col0;  // first column of this layer inside the positional projection buffer
   float scale_log2;  // log2(e) / sqrt(dk)
 };
 
@@ -65,7 +75,7 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (i0 >= len) {
     // the whole query tile is padding: context is zero (block-uniform exit, nothing allocated yet)
-    if (warp >= 2) {
+    if (warp >= 4 && warp < 8) {
       const int i = i0 + (warp & 3) * 32 + lane;
       if (i < T) {
         uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(b) * T + i) * p.Dp + h * kDK);
@@ -80,16 +90,17 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQu = smem;
   uint8_t* sQv = smem + kQBytes;
-  uint8_t* sP = smem + kOffP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* sg_full = bars + 5;   // [2]
-  uint64_t* sg_free = bars + 7;   // [2]
-  uint64_t* p_ready = bars + 9;
-  uint64_t* o_full = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* sg_full = bars + 1;   // [2] per softmax set
+  uint64_t* sg_free = bars + 3;   // [2]
+  uint64_t* p_ready = bars + 5;   // [2]
+  uint64_t* o_full = bars + 7;    // [2]
+  uint64_t* kv_full = bars + 9;                   // [kKVStages]
+  uint64_t* kv_empty = kv_full + kKVStages;       // [kKVStages]
+  uint64_t* band_full = kv_empty + kKVStages;     // [kBandBlocks]
+  uint64_t* band_empty = band_full + kBandBlocks; // [kBandBlocks]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(band_empty + kBandBlocks);
 
   const int n_kt = (len + kBN - 1) / kBN;
 
@@ -99,14 +110,20 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::prefetch_tmap(&tmKV);
       ptx::prefetch_tmap(&tmP);
       ptx::mbar_init(q_full, 1);
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < kKVStages; ++s) {
         ptx::mbar_init(&kv_full[s], 1);
         ptx::mbar_init(&kv_empty[s], 1);
+      }
+      for (int s = 0; s < kBandBlocks; ++s) {
+        ptx::mbar_init(&band_full[s], 1);
+        ptx::mbar_init(&band_empty[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&sg_full[s], 1);
         ptx::mbar_init(&sg_free[s], 128);
+        ptx::mbar_init(&p_ready[s], 128);
+        ptx::mbar_init(&o_full[s], 1);
       }
-      ptx::mbar_init(p_ready, 128);
-      ptx::mbar_init(o_full, 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -117,6 +134,8 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
   if (warp == 0) {
     // ---------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -124,119 +143,181 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::mbar_arrive_expect_tx(q_full, 2 * kQBytes);
       ptx::tma_load_2d(sQu, &tmQ, q_full, h * kDK, row_q);
       ptx::tma_load_2d(sQv, &tmQ, q_full, p.Dp + h * kDK, row_q);
+      const int r0 = T - 1 - i0 - (kBM - 1);  // band row of G column 0 for key tile 0 (may be < 0: TMA zero-fills)
+      auto load_band_block = [&](int g) {     // block g = band rows r0 + 64 g .. + 63, first needed by key tile g - 2
+        const int slot = g % kBandBlocks, use = g / kBandBlocks;
+        ptx::mbar_wait(&band_empty[slot], (use & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&band_full[slot], kBlockBytes);
+        ptx::tma_load_2d(smem + kOffBand + slot * kBlockBytes, &tmP, &band_full[slot], h * kDK, r0 + 64 * g);
+      };
+      load_band_block(0);
+      load_band_block(1);
       for (int kt = 0; kt < n_kt; ++kt) {
-        const int s = kt & 1;
-        ptx::mbar_wait(&kv_empty[s], ((kt >> 1) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&kv_full[s], kStageBytes);
-        uint8_t* st = smem + kOffStage + s * kStageBytes;
-        const int j0 = kt * kBN;
-        ptx::tma_load_2d(st, &tmKV, &kv_full[s], 2 * p.Dp + h * kDK, b * T + j0);
-        ptx::tma_load_2d(st + kKBytes, &tmKV, &kv_full[s], 3 * p.Dp + h * kDK, b * T + j0);
-        const int r_lo = T - 1 + j0 - i0 - (kBM - 1);  // band row of G column 0 (may be < 0: TMA zero-fills)
-#pragma unroll
-        for (int q = 0; q < kBand / 64; ++q)
-          ptx::tma_load_2d(st + 2 * kKBytes + q * (64 * kDK * 2), &tmP, &kv_full[s], p.pos_col0 + h * kDK,
-                           r_lo + q * 64);
+        const int st = kt % kKVStages, use = kt / kKVStages;
+        ptx::mbar_wait(&kv_empty[st], (use & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&kv_full[st], kKVBytes);
+        uint8_t* dst = smem + kOffKV + st * kKVBytes;
+        ptx::tma_load_2d(dst, &tmKV, &kv_full[st], 2 * p.Dp + h * kDK, b * T + kt * kBN);
+        ptx::tma_load_2d(dst + kKBytes, &tmKV, &kv_full[st], 3 * p.Dp + h * kDK, b * T + kt * kBN);
+        load_band_block(kt + 2);
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(kBM, kBN, 0, 0);
-      constexpr uint32_t idesc_g = ptx::make_idesc_bf16(kBM, kBand, 0, 0);
+      constexpr uint32_t idesc_g192 = ptx::make_idesc_bf16(kBM, 192, 0, 0);
+      constexpr uint32_t idesc_g128 = ptx::make_idesc_bf16(kBM, 128, 0, 0);
+      constexpr uint32_t idesc_g64 = ptx::make_idesc_bf16(kBM, 64, 0, 0);
+      const uint32_t band_base = ptx::smem_u32(smem + kOffBand);
+      auto band_ready = [&](int g) { return ptx::mbar_test(&band_full[g % kBandBlocks], (g / kBandBlocks) & 1); };
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16(kBM, kDK, 0, 1);  // B = V is MN-major (keys x dk rows)
       const uint64_t dQu = ptx::make_sdesc_sw128(ptx::smem_u32(sQu), 16, 1024);
       const uint64_t dQv = ptx::make_sdesc_sw128(ptx::smem_u32(sQv), 16, 1024);
-      const uint64_t dP = ptx::make_sdesc_sw128(ptx::smem_u32(sP), 16, 1024);
       ptx::mbar_wait(q_full, 0);
 
-      auto issue_sg = [&](int kt) {
-        const int s = kt & 1;
-        ptx::mbar_wait(&kv_full[s], (kt >> 1) & 1);
-        ptx::mbar_wait(&sg_free[s], ((kt >> 1) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t st = ptx::smem_u32(smem + kOffStage + s * kStageBytes);
-        const uint64_t dK = ptx::make_sdesc_sw128(st, 16, 1024);
-        const uint64_t dB = ptx::make_sdesc_sw128(st + 2 * kKBytes, 16, 1024);
-        const uint32_t tS = tmem_base + s * 256;
+      // Event loop: the two softmax sets advance independently, so the issuer serves whichever of
+      // {S/G of set s can be issued, P of set s is ready} fires first instead of blocking on one barrier.
+      int sg_next[2] = {0, 1};
+      int pv_next[2] = {0, 1};
+      int remaining = 2 * n_kt;
+      long long t_idle = 0;
+      while (remaining > 0) {
+        bool progressed = false;
 #pragma unroll
-        for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS, dQu + 2 * k, dK + 2 * k, idesc_s, k != 0);
+        for (int s = 0; s < 2; ++s) {
+          int kt = sg_next[s];
+          if (kt < n_kt) {
+            const int it = kt >> 1;
+            const int kvs = kt % kKVStages;
+            if (ptx::mbar_test(&kv_full[kvs], (kt / kKVStages) & 1) && ptx::mbar_test(&sg_free[s], (it & 1) ^ 1) &&
+                band_ready(kt + 2) && band_ready(kt + 1) && band_ready(kt)) {
+              ptx::tc_fence_after();
+              const uint64_t dK = ptx::make_sdesc_sw128(ptx::smem_u32(smem + kOffKV + kvs * kKVBytes), 16, 1024);
+              const uint32_t tS = tmem_base + s * 256;
 #pragma unroll
-        for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN, dQv + 2 * k, dB + 2 * k, idesc_g, k != 0);
-        ptx::tc_commit(&sg_full[s]);
-      };
-
-      issue_sg(0);
-      for (int kt = 0; kt < n_kt; ++kt) {
-        const int s = kt & 1;
-        if (kt + 1 < n_kt) issue_sg(kt + 1);
-        ptx::mbar_wait(p_ready, kt & 1);
-        ptx::tc_fence_after();
-        const uint32_t st = ptx::smem_u32(smem + kOffStage + s * kStageBytes);
-        // V tile: 64 keys (K of this MMA) x 64 dk (N), 128-byte rows along N -> MN-major, 8-key groups 1024 B apart
-        const uint64_t dV = ptx::make_sdesc_sw128(st + kKBytes, 1024, 1024);
+              for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS, dQu + 2 * k, dK + 2 * k, idesc_s, k != 0);
+              // G = (Q+v) band^T over ring blocks kt, kt+1, kt+2: one 192-wide MMA group, or two when the ring wraps
+              const int s0 = kt % kBandBlocks, s1 = (kt + 1) % kBandBlocks, s2 = (kt + 2) % kBandBlocks;
+              const uint64_t d0 = ptx::make_sdesc_sw128(band_base + s0 * kBlockBytes, 16, 1024);
+              if (s1 == s0 + 1 && s2 == s1 + 1) {
 #pragma unroll
-        for (int k = 0; k < kBN / 16; ++k)
-          ptx::umma_bf16(tmem_base + s * 256, dP + 2 * k, dV + static_cast<uint64_t>(k) * (2048 >> 4), idesc_o, k != 0);
-        ptx::tc_commit(o_full);
-        ptx::tc_commit(&kv_empty[s]);
+                for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN, dQv + 2 * k, d0 + 2 * k, idesc_g192, k != 0);
+              } else if (s1 != s0 + 1) {  // wrap after the first block
+                const uint64_t d1 = ptx::make_sdesc_sw128(band_base + s1 * kBlockBytes, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN, dQv + 2 * k, d0 + 2 * k, idesc_g64, k != 0);
+#pragma unroll
+                for (int k = 0; k < kDK / 16; ++k)
+                  ptx::umma_bf16(tS + kBN + 64, dQv + 2 * k, d1 + 2 * k, idesc_g128, k != 0);
+              } else {  // wrap after the second block
+                const uint64_t d2 = ptx::make_sdesc_sw128(band_base + s2 * kBlockBytes, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN, dQv + 2 * k, d0 + 2 * k, idesc_g128, k != 0);
+#pragma unroll
+                for (int k = 0; k < kDK / 16; ++k)
+                  ptx::umma_bf16(tS + kBN + 128, dQv + 2 * k, d2 + 2 * k, idesc_g64, k != 0);
+              }
+              ptx::tc_commit(&sg_full[s]);
+              ptx::tc_commit(&band_empty[s0]);  // block kt is not read by any later tile
+              sg_next[s] = kt + 2;
+              --remaining;
+              progressed = true;
+            }
+          }
+          kt = pv_next[s];
+          if (kt < n_kt && kt < sg_next[s]) {
+            const int it = kt >> 1;
+            if (ptx::mbar_test(&p_ready[s], it & 1)) {
+              ptx::tc_fence_after();
+              const int kvs = kt % kKVStages;
+              const uint32_t st = ptx::smem_u32(smem + kOffKV + kvs * kKVBytes);
+              const uint64_t dP = ptx::make_sdesc_sw128(ptx::smem_u32(smem + kOffP + s * kPBytes), 16, 1024);
+              // V tile: 64 keys (K of this MMA) x 64 dk (N), 128-byte rows along N -> MN-major, 8-key groups 1 KB apart
+              const uint64_t dV = ptx::make_sdesc_sw128(st + kKBytes, 1024, 1024);
+#pragma unroll
+              for (int k = 0; k < kBN / 16; ++k)
+                ptx::umma_bf16(tmem_base + s * 256, dP + 2 * k, dV + static_cast<uint64_t>(k) * (2048 >> 4), idesc_o,
+                               k != 0);
+              ptx::tc_commit(&o_full[s]);
+              ptx::tc_commit(&kv_empty[kvs]);
+              pv_next[s] = kt + 2;
+              --remaining;
+              progressed = true;
+            }
+          }
+        }
+        if (progressed) {
+          t_idle = 0;
+        } else {
+          if (t_idle == 0) t_idle = clock64();
+          else if (clock64() - t_idle > CFB_MBAR_TIMEOUT_CYCLES) __trap();
+        }
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
     // ---------------------------------------------------------------------------------- softmax warps
     const int quarter = warp & 3;
+    const int set = (warp - 4) >> 2;
     const int ii = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     const int i = i0 + ii;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + set * 256;
     const int g_base = kBN + (96 - 32 * quarter);  // warp-uniform part of the rel_shift column offset
-    const int sh = 31 - lane;                      // per-lane part, applied by the barrel shifter
+    const int sh = 31 - lane;                      // per-lane part, applied through the private smem row
+    const uint32_t shift_row = ptx::smem_u32(smem + kOffShift + (warp - 4) * kShiftBytes) + lane * kShiftPitch * 4;
+    const uint32_t prow = ptx::smem_u32(smem + kOffP + set * kPBytes) + ii * 128;
     float o_acc[kDK];
 #pragma unroll
     for (int c = 0; c < kDK; ++c) o_acc[c] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_pending = 1.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
 
-    for (int kt = 0; kt < n_kt; ++kt) {
-      const int s = kt & 1;
+    auto fold_o_part = [&]() {  // o_acc = o_acc * alpha_prev + O_part (the S columns of this set's buffer)
+      uint32_t a0[32], a1[32];
+      ptx::tmem_ld_x32(tS, a0);
+      ptx::tmem_ld_x32(tS + 32, a1);
+      ptx::tc_wait_ld();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        o_acc[c] = fmaf(o_acc[c], alpha_prev, __uint_as_float(a0[c]));
+        o_acc[32 + c] = fmaf(o_acc[32 + c], alpha_prev, __uint_as_float(a1[c]));
+      }
+    };
+
+    int it = 0;
+    for (int kt = set; kt < n_kt; kt += 2, ++it) {
       const int j0 = kt * kBN;
-      ptx::mbar_wait(&sg_full[s], (kt >> 1) & 1);
+      if (it > 0) {
+        ptx::mbar_wait(&o_full[set], (it - 1) & 1);
+        ptx::tc_fence_after();
+        fold_o_part();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&sg_free[set]);  // the buffer may now receive the S / G of this tile
+      }
+      ptx::mbar_wait(&sg_full[set], it & 1);
       ptx::tc_fence_after();
-      const uint32_t tS = lane_addr + s * 256;
       float sv[kBN];
 #pragma unroll
-      for (int qd = 0; qd < kBN / 16; ++qd) {
-        uint32_t a[16], w[48];
-        ptx::tmem_ld_x16(tS + qd * 16, a);
-        ptx::tmem_ld_x16(tS + g_base + qd * 16, w);
-        ptx::tmem_ld_x16(tS + g_base + qd * 16 + 16, w + 16);
-        ptx::tmem_ld_x16(tS + g_base + qd * 16 + 32, w + 32);
+      for (int hf = 0; hf < 2; ++hf) {  // 32 keys at a time: window of 63 columns through the private row
+        uint32_t w0[32], w1[32], a[32];
+        ptx::tmem_ld_x32(tS + g_base + hf * 32, w0);       // all loads of this half in flight, one wait
+        ptx::tmem_ld_x32(tS + g_base + hf * 32 + 32, w1);
+        ptx::tmem_ld_x32(tS + hf * 32, a);
         ptx::tc_wait_ld();
-        // out[jj] = w[jj + sh], sh in [0,31]
-        if (sh & 16) {
 #pragma unroll
-          for (int c = 0; c < 31; ++c) w[c] = w[c + 16];
-        }
-        if (sh & 8) {
-#pragma unroll
-          for (int c = 0; c < 23; ++c) w[c] = w[c + 8];
-        }
-        if (sh & 4) {
-#pragma unroll
-          for (int c = 0; c < 19; ++c) w[c] = w[c + 4];
-        }
-        if (sh & 2) {
-#pragma unroll
-          for (int c = 0; c < 17; ++c) w[c] = w[c + 2];
-        }
-        if (sh & 1) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) w[c] = w[c + 1];
+        for (int v4 = 0; v4 < 8; ++v4) {
+          ptx::sts128(shift_row + v4 * 16, w0[4 * v4], w0[4 * v4 + 1], w0[4 * v4 + 2], w0[4 * v4 + 3]);
+          ptx::sts128(shift_row + 128 + v4 * 16, w1[4 * v4], w1[4 * v4 + 1], w1[4 * v4 + 2], w1[4 * v4 + 3]);
         }
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int j = j0 + qd * 16 + c;
-          const float x = (__uint_as_float(a[c]) + __uint_as_float(w[c])) * p.scale_log2;
-          sv[qd * 16 + c] = (j < len) ? x : -INFINITY;
-        }
+        for (int c = 0; c < 32; ++c)
+          sv[hf * 32 + c] = (__uint_as_float(a[c]) + ptx::lds_f32(shift_row + (sh + c) * 4)) * p.scale_log2;
+      }
+      if (j0 + kBN > len) {  // only the last key tile can contain masked keys
+#pragma unroll
+        for (int c = 0; c < kBN; ++c)
+          if (j0 + c >= len) sv[c] = -INFINITY;
       }
       float mx = sv[0];
 #pragma unroll
@@ -249,71 +330,54 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         sv[c] = fast_exp2(sv[c] - m_new);
         rsum += sv[c];
       }
-      l_run = l_run * alpha + rsum;
+      l_run = fmaf(l_run, alpha, rsum);
       m_run = m_new;
-
-      // the probability tile is single-buffered: PV of the previous key tile must have drained it
-      if (kt > 0) {
-        ptx::mbar_wait(o_full, (kt - 1) & 1);
-        ptx::tc_fence_after();
-      }
-      {
-        uint8_t* prow = sP + ii * 128;
+      alpha_prev = alpha;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint4 u;
-          u.x = ptx::pack_bf16x2(sv[8 * c + 0], sv[8 * c + 1]);
-          u.y = ptx::pack_bf16x2(sv[8 * c + 2], sv[8 * c + 3]);
-          u.z = ptx::pack_bf16x2(sv[8 * c + 4], sv[8 * c + 5]);
-          u.w = ptx::pack_bf16x2(sv[8 * c + 6], sv[8 * c + 7]);
-          *reinterpret_cast<uint4*>(prow + ((c ^ (ii & 7)) << 4)) = u;  // 128-byte swizzle, K-major
-        }
+      for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        u.x = ptx::pack_bf16x2(sv[8 * c + 0], sv[8 * c + 1]);
+        u.y = ptx::pack_bf16x2(sv[8 * c + 2], sv[8 * c + 3]);
+        u.z = ptx::pack_bf16x2(sv[8 * c + 4], sv[8 * c + 5]);
+        u.w = ptx::pack_bf16x2(sv[8 * c + 6], sv[8 * c + 7]);
+        ptx::sts128(prow + ((c ^ (ii & 7)) << 4), u.x, u.y, u.z, u.w);  // 128-byte swizzle, K-major
       }
       ptx::fence_proxy_async_smem();
-      ptx::tc_fence_before();  // orders this thread's TMEM reads of S/G before the MMA that overwrites S
-      ptx::mbar_arrive(p_ready);
-
-      if (kt > 0) {
-        // fold in O_part of the previous tile (it sits in the S columns of the other TMEM buffer)
-        const uint32_t tO = lane_addr + ((kt - 1) & 1) * 256;
-#pragma unroll
-        for (int qd = 0; qd < kDK / 16; ++qd) {
-          uint32_t a[16];
-          ptx::tmem_ld_x16(tO + qd * 16, a);
-          ptx::tc_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 16; ++c) o_acc[qd * 16 + c] = o_acc[qd * 16 + c] * alpha_pending + __uint_as_float(a[c]);
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&sg_free[(kt - 1) & 1]);
-      }
-      alpha_pending = alpha;
+      ptx::tc_fence_before();  // orders this thread's TMEM reads of S/G before the PV MMA that overwrites S
+      ptx::mbar_arrive(&p_ready[set]);
     }
-    // drain the last tile
-    {
-      const int kt = n_kt - 1;
-      ptx::mbar_wait(o_full, kt & 1);
+    if (it > 0) {  // drain the last tile of this set
+      ptx::mbar_wait(&o_full[set], (it - 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t tO = lane_addr + (kt & 1) * 256;
-      const float inv = (i < len && l_run > 0.f) ? 1.f / l_run : 0.f;  // padded query rows -> zeros
+      fold_o_part();
+    }
+    // ---- merge the two sets (log-sum-exp) and write the context rows
+    const uint32_t xrow = ptx::smem_u32(smem + kOffShift + (quarter + 4) * kShiftBytes) + lane * kShiftPitch * 4;
+    if (set == 1) {
+      ptx::sts_f32(xrow, m_run);
+      ptx::sts_f32(xrow + 4, l_run);
 #pragma unroll
-      for (int qd = 0; qd < kDK / 16; ++qd) {
-        uint32_t a[16];
-        ptx::tmem_ld_x16(tO + qd * 16, a);
-        ptx::tc_wait_ld();
-#pragma unroll
-        for (int c = 0; c < 16; ++c)
-          o_acc[qd * 16 + c] = (o_acc[qd * 16 + c] * alpha_pending + __uint_as_float(a[c])) * inv;
-      }
+      for (int c = 0; c < kDK; ++c) ptx::sts_f32(xrow + 8 + 4 * c, o_acc[c]);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (set == 0) {
+      const float m1 = ptx::lds_f32(xrow), l1 = ptx::lds_f32(xrow + 4);
+      const float m = fmaxf(m_run, m1);  // set 0 always owns key tile 0, so m is finite
+      const float w0 = fast_exp2(m_run - m), w1 = fast_exp2(m1 - m);
+      const float l = l_run * w0 + l1 * w1;
+      const float inv = (i < len && l > 0.f) ? 1.f / l : 0.f;  // padded query rows -> zeros
       if (i < T) {
         uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(b) * T + i) * p.Dp + h * kDK);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
+          float r[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] = (o_acc[8 * c + e] * w0 + ptx::lds_f32(xrow + 8 + 4 * (8 * c + e)) * w1) * inv;
           uint4 u;
-          u.x = ptx::pack_bf16x2(o_acc[8 * c + 0], o_acc[8 * c + 1]);
-          u.y = ptx::pack_bf16x2(o_acc[8 * c + 2], o_acc[8 * c + 3]);
-          u.z = ptx::pack_bf16x2(o_acc[8 * c + 4], o_acc[8 * c + 5]);
-          u.w = ptx::pack_bf16x2(o_acc[8 * c + 6], o_acc[8 * c + 7]);
+          u.x = ptx::pack_bf16x2(r[0], r[1]);
+          u.y = ptx::pack_bf16x2(r[2], r[3]);
+          u.z = ptx::pack_bf16x2(r[4], r[5]);
+          u.w = ptx::pack_bf16x2(r[6], r[7]);
           o[c] = u;
         }
       }
@@ -370,7 +434,6 @@ int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
   p.ctx = reinterpret_cast<bf16*>(a.ctx);
   p.T = a.T;
   p.Dp = Dp;
-  p.pos_col0 = 0;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(a.dk));
   dim3 grid((a.T + kBM - 1) / kBM, a.H, a.B);
   rel_attn_tc_kernel<<<grid, kThreads, kSmemTotal, st>>>(tmQ, tmKV, tmP, p);

@@ -25,11 +25,12 @@ __device__ __forceinline__ void store4(bf16* p, float a, float b, float c, float
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// One warp per row; the row lives in registers (d <= 32*4*kMaxVec) between the two reduction passes, so x is read
-// from HBM exactly once.  Statistics in fp32: mean, then the centred second moment (matches F.layer_norm).
-constexpr int kMaxVec = 8;  // float4 per lane -> d <= 1024
+// One warp per row; the row lives in registers between the two reduction passes, so x is read from HBM exactly once.
+// Statistics in fp32: mean, then the centred second moment (matches F.layer_norm).  NV = float4 per lane
+// (d = 128*NV exactly) for the common widths; the generic instance (NV = 0) handles any d % 4 == 0 up to 1024.
+constexpr int kMaxVec = 8;
 
-template <typename TOut>
+template <typename TOut, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, TOut* __restrict__ out,
                                                         int rows, int d, const int32_t* __restrict__ lens,
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  constexpr int kN = NV > 0 ? NV : kMaxVec;
   const int nvec = d >> 2;  // float4 per row
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * d);
   TOut* orow = out + static_cast<long long>(row) * d;
@@ -47,41 +49,42 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       return;
     }
   }
-  float4 v[kMaxVec];
+  float4 v[kN];
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < kMaxVec; ++k) {
+  for (int k = 0; k < kN; ++k) {
     const int i = lane + 32 * k;
-    if (i < nvec) {
-      v[k] = xr[i];
+    if (NV > 0 || i < nvec) {
+      v[k] = __ldcs(xr + i);
       s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
     }
   }
-  const float mean = warp_sum(s) / static_cast<float>(d);
+  const float inv_d = 1.0f / static_cast<float>(d);
+  const float mean = warp_sum(s) * inv_d;
   float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < kMaxVec; ++k) {
+  for (int k = 0; k < kN; ++k) {
     const int i = lane + 32 * k;
-    if (i < nvec) {
-      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, e = v[k].w - mean;
-      q += (a * a + b * b) + (c * c + e * e);
+    if (NV > 0 || i < nvec) {
+      v[k].x -= mean, v[k].y -= mean, v[k].z -= mean, v[k].w -= mean;
+      q += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
     }
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(d) + 1e-5f);
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * inv_d + 1e-5f);
 #pragma unroll
-  for (int k = 0; k < kMaxVec; ++k) {
+  for (int k = 0; k < kN; ++k) {
     const int i = lane + 32 * k;
-    if (i < nvec) {
+    if (NV > 0 || i < nvec) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
       const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i);
-      store4(orow + 4 * i, (v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y,
-             (v[k].z - mean) * rstd * g.z + b.z, (v[k].w - mean) * rstd * g.w + b.w);
+      store4(orow + 4 * i, fmaf(v[k].x * rstd, g.x, b.x), fmaf(v[k].y * rstd, g.y, b.y),
+             fmaf(v[k].z * rstd, g.z, b.z), fmaf(v[k].w * rstd, g.w, b.w));
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ depth-wise conv
-// out[b,t,c] = swish(bias[c] + sum_k taps[c][k] * x[b, t + k - (K-1)/2, c]), zero outside [0,T).
+// out[b,t,c] = swish(bias[c] + sum_k taps[k][c] * x[b, t + k - (K-1)/2, c]), zero outside [0,T); taps are (K, d).
 // Block: 64 channels x 128 frames of one sequence.  The (128 + K - 1)-frame halo tile is staged in shared memory in
 // the activation dtype with 16-byte cp.async copies (all in flight at once); each thread owns a channel pair and 16
 // consecutive frames and slides the K-tap window over registers.  Reads and writes are 128-byte row segments.
@@ -100,6 +103,18 @@ __device__ __forceinline__ float2 load2<bf16>(const bf16* p) {
 __device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void store2(bf16* p, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+// d = a * b + c on two packed fp32 lanes (sm_100 FFMA2): the channel pair of a thread is one 64-bit register pair
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
 }
 
 template <typename T, bool kFast>
@@ -139,19 +154,20 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const T* __restrict__ x,
   const int strip = threadIdx.x >> 5;  // 8 strips of 16 frames
   const int c = c0 + 2 * cp;
   const bool live = c < d;
-  float w0[kDwMaxK], w1[kDwMaxK];
+  float2 w[kDwMaxK];
 #pragma unroll
   for (int k = 0; k < kDwMaxK; ++k) {
-    w0[k] = (live && k < ksize) ? __ldg(taps + static_cast<long long>(c) * ksize + k) : 0.f;
-    w1[k] = (live && k < ksize) ? __ldg(taps + static_cast<long long>(c + 1) * ksize + k) : 0.f;
+    // taps are stored tap-major (ksize, d): a warp reads 256 contiguous bytes per tap
+    w[k] = (live && k < ksize) ? __ldg(reinterpret_cast<const float2*>(taps + static_cast<long long>(k) * d + c))
+                               : make_float2(0.f, 0.f);
   }
   const float b0 = live ? __ldg(bias + c) : 0.f, b1 = live ? __ldg(bias + c + 1) : 0.f;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (!live) return;
-  float a0[kDwStrip], a1[kDwStrip];
+  float2 acc[kDwStrip];
 #pragma unroll
-  for (int o = 0; o < kDwStrip; ++o) a0[o] = b0, a1[o] = b1;
+  for (int o = 0; o < kDwStrip; ++o) acc[o] = make_float2(b0, b1);
 #pragma unroll
   for (int j = 0; j < kDwStrip + kDwMaxK - 1; ++j) {
     if (j < kDwStrip + ksize - 1) {
@@ -159,10 +175,7 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const T* __restrict__ x,
 #pragma unroll
       for (int o = 0; o < kDwStrip; ++o) {
         const int k = j - o;
-        if (k >= 0 && k < kDwMaxK) {
-          a0[o] = fmaf(w0[k], vv.x, a0[o]);
-          a1[o] = fmaf(w1[k], vv.y, a1[o]);
-        }
+        if (k >= 0 && k < kDwMaxK) acc[o] = fma2(w[k], vv, acc[o]);
       }
     }
   }
@@ -171,12 +184,16 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const T* __restrict__ x,
     const int t = t0 + strip * kDwStrip + o;
     if (t < T_len) {
       float s0, s1;
-      if constexpr (kFast) {
-        s0 = __fdividef(a0[o], 1.f + __expf(-a0[o]));
-        s1 = __fdividef(a1[o], 1.f + __expf(-a1[o]));
+      if constexpr (kFast) {  // swish(x) = h + h tanh(h), h = x/2
+        const float h0 = 0.5f * acc[o].x, h1 = 0.5f * acc[o].y;
+        float t0f, t1f;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t0f) : "f"(h0));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t1f) : "f"(h1));
+        s0 = fmaf(h0, t0f, h0);
+        s1 = fmaf(h1, t1f, h1);
       } else {
-        s0 = a0[o] / (1.f + expf(-a0[o]));
-        s1 = a1[o] / (1.f + expf(-a1[o]));
+        s0 = acc[o].x / (1.f + expf(-acc[o].x));
+        s1 = acc[o].y / (1.f + expf(-acc[o].y));
       }
       store2(ob + static_cast<long long>(t) * d + c, s0, s1);
     }
@@ -318,12 +335,19 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
   if (rows <= 0) return 0;
   if (d % 4 != 0 || d > 128 * kMaxVec) return -1;
   const int blocks = (rows + 7) / 8;
-  if (out_bf16)
-    layernorm_kernel<bf16><<<blocks, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<bf16*>(out), rows, d, lens,
-                                                   frames_per_seq);
-  else
-    layernorm_kernel<float><<<blocks, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<float*>(out), rows, d, lens,
-                                                    frames_per_seq);
+#define CFB_LN(T, NV)                                                                                          \
+  layernorm_kernel<T, NV><<<blocks, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<T*>(out), rows, d, lens,   \
+                                                  frames_per_seq)
+  if (out_bf16) {
+    if (d == 512) CFB_LN(bf16, 4);
+    else if (d == 256) CFB_LN(bf16, 2);
+    else CFB_LN(bf16, 0);
+  } else {
+    if (d == 512) CFB_LN(float, 4);
+    else if (d == 256) CFB_LN(float, 2);
+    else CFB_LN(float, 0);
+  }
+#undef CFB_LN
   return static_cast<int>(cudaGetLastError());
 }
 

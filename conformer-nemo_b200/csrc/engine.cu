@@ -450,7 +450,7 @@ int cfb_finalize_weights(cfb_handle* h) {
       std::vector<float> taps(static_cast<size_t>(d) * ks), bias(d);
       for (int ch = 0; ch < d; ++ch) {
         const double s = static_cast<double>(bng->data[ch]) / sqrt(static_cast<double>(bnv->data[ch]) + 1e-5);
-        for (int k = 0; k < ks; ++k) taps[static_cast<size_t>(ch) * ks + k] = static_cast<float>(dww->data[ch * ks + k] * s);
+        for (int k = 0; k < ks; ++k) taps[static_cast<size_t>(k) * d + ch] = static_cast<float>(dww->data[ch * ks + k] * s);  // tap-major
         bias[ch] = static_cast<float>((static_cast<double>(dwb->data[ch]) - bnm->data[ch]) * s + bnb->data[ch]);
       }
       lw.dw_taps = ab.put_f32(taps);

@@ -58,12 +58,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     if (done) break;
     if (++spins == 1024u) t0 = clock64();
-    if (spins > 1024u && (spins & 1023u) == 0 && clock64() - t0 > CFB_MBAR_TIMEOUT_CYCLES) {
-      printf("cfb: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x,
-             parity);
-      __trap();
-    }
+    if (spins > 1024u && (spins & 1023u) == 0 && clock64() - t0 > CFB_MBAR_TIMEOUT_CYCLES) __trap();
   }
+}
+
+// non-blocking probe of a phase (used by event loops that serve several barriers)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
@@ -199,6 +210,19 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+
+// explicit shared-space accesses (the compiler falls back to generic LD/ST when it cannot prove the address space)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -150,7 +150,8 @@ CFB_API int cfb_op_layernorm(const float* x, const float* gamma, const float* be
                      int d, const int32_t* lens, int frames_per_seq, cfb_stream stream);
 
 /* Depth-wise time convolution with folded BatchNorm + Swish (conformer_modules.py:168-177).
- * x, out: (B, T, d) in `dtype` (CFB_BF16 / CFB_F32); taps (d, ksize) fp32; bias (d) fp32; zero padding at both ends. */
+ * x, out: (B, T, d) in `dtype` (CFB_BF16 / CFB_F32); taps (ksize, d) fp32, tap-major; bias (d) fp32; zero padding at
+ * both ends of every sequence. */
 CFB_API int cfb_op_depthwise(const void* x, const float* taps, const float* bias, void* out, int dtype, int B, int T, int d,
                      int ksize, cfb_stream stream);
 

@@ -42,9 +42,11 @@ def op_layernorm(x, gamma, beta, out, lens=None, frames_per_seq=1):
 
 
 def op_depthwise(x, taps, bias, out):
+    """taps given as (d, ksize) like the reference's depthwise_conv.weight; the kernel wants them tap-major."""
     lib = _lib.load_library()
     B, T, d = x.shape
-    rc = lib.cfb_op_depthwise(ptr(x), ptr(taps), ptr(bias), ptr(out), DT[x.dtype], B, T, d, taps.shape[1], stream())
+    taps_km = taps.t().contiguous()
+    rc = lib.cfb_op_depthwise(ptr(x), ptr(taps_km), ptr(bias), ptr(out), DT[x.dtype], B, T, d, taps.shape[1], stream())
     assert rc == 0, _lib.last_error(None)
     torch.cuda.synchronize()
     return out
