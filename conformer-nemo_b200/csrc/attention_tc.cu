@@ -6,8 +6,10 @@
 //   warp 0      TMA producer: Q+u, Q+v once; per 64-key tile K and V (3-stage ring) and the 64 NEW rows of the
 //               192-row band of linear_pos(pos_emb) the tile can touch (rows T-1+j0-i0-127 .. +191): consecutive key
 //               tiles share two thirds of their band, so the band lives in a 5-block ring of 64-row blocks
-//   warp 1      MMA issuer (tcgen05, cta_group::1): S = (Q+u) K^T (128x64) and G = (Q+v) Pband^T (128x192) into the
-//               TMEM buffer of the tile's set, later O_part = P V (128x64) into the S columns of the same buffer
+//   warps 1, 2  MMA issuers (tcgen05, cta_group::1), one per softmax set: S = (Q+u) K^T (128x64) and
+//               G = (Q+v) Pband^T (128x192) into the set's TMEM buffer, later O_part = P V (128x64) into the S
+//               columns of the same buffer.  Within a set the order S/G -> P V -> next S/G is a chain, so each
+//               issuer simply blocks on its own barriers while the other set's issuer proceeds
 //   warps 4..11 two softmax sets of four warps (one query row per thread).  Set s owns key tiles s, s+2, ... with its
 //               own TMEM buffer, probability tile and running (max, sum, O); the sets ping-pong so one set's exp /
 //               shift work overlaps the other's MMAs, and are merged (log-sum-exp) at the end.
@@ -19,6 +21,7 @@
 // i >= len[b] are written as zeros (multi_head_attention.py:104-113).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -54,6 +57,8 @@ struct AttnParams {
   bf16* ctx;
   int T, Dp;
   float scale_log2;  // log2(e) / sqrt(dk)
+  int debug;         // CFB_ATTN_DEBUG ablation bits (timing experiments only; results are wrong when non-zero)
+  long long* trace;  // debug bit 8: clock64 trace of CTA (0,0,0): [0..] softmax warp 4 lane 0, [512..] issuer of set 0
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -92,11 +97,12 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* sQv = smem + kQBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* sg_full = bars + 1;   // [2] per softmax set
-  uint64_t* sg_free = bars + 3;   // [2]
-  uint64_t* p_ready = bars + 5;   // [2]
-  uint64_t* o_full = bars + 7;    // [2]
-  uint64_t* kv_full = bars + 9;                   // [kKVStages]
+  uint64_t* sg_full = bars + 1;   // [2] per softmax set: S and G of the set's current key tile are in TMEM
+  uint64_t* s_free = bars + 3;    // [2] O_part folded: the S columns may be overwritten
+  uint64_t* g_free = bars + 5;    // [2] G window loaded: the G columns may be overwritten (next tile's G issued early)
+  uint64_t* p_ready = bars + 7;   // [2]
+  uint64_t* o_full = bars + 9;    // [2]
+  uint64_t* kv_full = bars + 11;                  // [kKVStages]
   uint64_t* kv_empty = kv_full + kKVStages;       // [kKVStages]
   uint64_t* band_full = kv_empty + kKVStages;     // [kBandBlocks]
   uint64_t* band_empty = band_full + kBandBlocks; // [kBandBlocks]
@@ -120,8 +126,9 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       for (int s = 0; s < 2; ++s) {
         ptx::mbar_init(&sg_full[s], 1);
-        ptx::mbar_init(&sg_free[s], 128);
-        ptx::mbar_init(&p_ready[s], 128);
+        ptx::mbar_init(&s_free[s], 4);   // one elected arrival per softmax warp
+        ptx::mbar_init(&g_free[s], 4);
+        ptx::mbar_init(&p_ready[s], 4);
         ptx::mbar_init(&o_full[s], 1);
       }
       ptx::fence_mbar_init();
@@ -162,97 +169,82 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         load_band_block(kt + 2);
       }
     }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || warp == 2) {
+    // ---------------------------------------------------------------------------------- MMA issuer of set (warp-1)
     if (lane == 0) {
+      const int s = warp - 1;
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(kBM, kBN, 0, 0);
       constexpr uint32_t idesc_g192 = ptx::make_idesc_bf16(kBM, 192, 0, 0);
       constexpr uint32_t idesc_g128 = ptx::make_idesc_bf16(kBM, 128, 0, 0);
       constexpr uint32_t idesc_g64 = ptx::make_idesc_bf16(kBM, 64, 0, 0);
-      const uint32_t band_base = ptx::smem_u32(smem + kOffBand);
-      auto band_ready = [&](int g) { return ptx::mbar_test(&band_full[g % kBandBlocks], (g / kBandBlocks) & 1); };
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16(kBM, kDK, 0, 1);  // B = V is MN-major (keys x dk rows)
       const uint64_t dQu = ptx::make_sdesc_sw128(ptx::smem_u32(sQu), 16, 1024);
       const uint64_t dQv = ptx::make_sdesc_sw128(ptx::smem_u32(sQv), 16, 1024);
+      const uint64_t dP = ptx::make_sdesc_sw128(ptx::smem_u32(smem + kOffP + s * kPBytes), 16, 1024);
+      const uint32_t band_base = ptx::smem_u32(smem + kOffBand);
+      const uint32_t tS = tmem_base + s * 256;
       ptx::mbar_wait(q_full, 0);
-
-      // Event loop: the two softmax sets advance independently, so the issuer serves whichever of
-      // {S/G of set s can be issued, P of set s is ready} fires first instead of blocking on one barrier.
-      int sg_next[2] = {0, 1};
-      int pv_next[2] = {0, 1};
-      int remaining = 2 * n_kt;
-      long long t_idle = 0;
-      while (remaining > 0) {
-        bool progressed = false;
+      // G = (Q+v) band^T over ring blocks kt, kt+1, kt+2: one 192-wide MMA group, or two when the ring wraps.
+      // Issued one tile ahead (as soon as the set has loaded the previous G window), so only the short S MMA and
+      // the P V MMA sit on the set's critical path.
+      auto issue_g = [&](int kt) {
+        for (int g = kt; g <= kt + 2; ++g) ptx::mbar_wait(&band_full[g % kBandBlocks], (g / kBandBlocks) & 1);
+        ptx::tc_fence_after();
+        const int s0 = kt % kBandBlocks, s1 = (kt + 1) % kBandBlocks, s2 = (kt + 2) % kBandBlocks;
+        const uint64_t d0 = ptx::make_sdesc_sw128(band_base + s0 * kBlockBytes, 16, 1024);
+        if (s1 == s0 + 1 && s2 == s1 + 1) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          int kt = sg_next[s];
-          if (kt < n_kt) {
-            const int it = kt >> 1;
-            const int kvs = kt % kKVStages;
-            if (ptx::mbar_test(&kv_full[kvs], (kt / kKVStages) & 1) && ptx::mbar_test(&sg_free[s], (it & 1) ^ 1) &&
-                band_ready(kt + 2) && band_ready(kt + 1) && band_ready(kt)) {
-              ptx::tc_fence_after();
-              const uint64_t dK = ptx::make_sdesc_sw128(ptx::smem_u32(smem + kOffKV + kvs * kKVBytes), 16, 1024);
-              const uint32_t tS = tmem_base + s * 256;
+          for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN, dQv + 2 * k, d0 + 2 * k, idesc_g192, k != 0);
+        } else if (s1 != s0 + 1) {  // wrap after the first block
+          const uint64_t d1 = ptx::make_sdesc_sw128(band_base + s1 * kBlockBytes, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS, dQu + 2 * k, dK + 2 * k, idesc_s, k != 0);
-              // G = (Q+v) band^T over ring blocks kt, kt+1, kt+2: one 192-wide MMA group, or two when the ring wraps
-              const int s0 = kt % kBandBlocks, s1 = (kt + 1) % kBandBlocks, s2 = (kt + 2) % kBandBlocks;
-              const uint64_t d0 = ptx::make_sdesc_sw128(band_base + s0 * kBlockBytes, 16, 1024);
-              if (s1 == s0 + 1 && s2 == s1 + 1) {
+          for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN, dQv + 2 * k, d0 + 2 * k, idesc_g64, k != 0);
 #pragma unroll
-                for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN, dQv + 2 * k, d0 + 2 * k, idesc_g192, k != 0);
-              } else if (s1 != s0 + 1) {  // wrap after the first block
-                const uint64_t d1 = ptx::make_sdesc_sw128(band_base + s1 * kBlockBytes, 16, 1024);
+          for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN + 64, dQv + 2 * k, d1 + 2 * k, idesc_g128, k != 0);
+        } else {  // wrap after the second block
+          const uint64_t d2 = ptx::make_sdesc_sw128(band_base + s2 * kBlockBytes, 16, 1024);
 #pragma unroll
-                for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN, dQv + 2 * k, d0 + 2 * k, idesc_g64, k != 0);
+          for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN, dQv + 2 * k, d0 + 2 * k, idesc_g128, k != 0);
 #pragma unroll
-                for (int k = 0; k < kDK / 16; ++k)
-                  ptx::umma_bf16(tS + kBN + 64, dQv + 2 * k, d1 + 2 * k, idesc_g128, k != 0);
-              } else {  // wrap after the second block
-                const uint64_t d2 = ptx::make_sdesc_sw128(band_base + s2 * kBlockBytes, 16, 1024);
-#pragma unroll
-                for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN, dQv + 2 * k, d0 + 2 * k, idesc_g128, k != 0);
-#pragma unroll
-                for (int k = 0; k < kDK / 16; ++k)
-                  ptx::umma_bf16(tS + kBN + 128, dQv + 2 * k, d2 + 2 * k, idesc_g64, k != 0);
-              }
-              ptx::tc_commit(&sg_full[s]);
-              ptx::tc_commit(&band_empty[s0]);  // block kt is not read by any later tile
-              sg_next[s] = kt + 2;
-              --remaining;
-              progressed = true;
-            }
-          }
-          kt = pv_next[s];
-          if (kt < n_kt && kt < sg_next[s]) {
-            const int it = kt >> 1;
-            if (ptx::mbar_test(&p_ready[s], it & 1)) {
-              ptx::tc_fence_after();
-              const int kvs = kt % kKVStages;
-              const uint32_t st = ptx::smem_u32(smem + kOffKV + kvs * kKVBytes);
-              const uint64_t dP = ptx::make_sdesc_sw128(ptx::smem_u32(smem + kOffP + s * kPBytes), 16, 1024);
-              // V tile: 64 keys (K of this MMA) x 64 dk (N), 128-byte rows along N -> MN-major, 8-key groups 1 KB apart
-              const uint64_t dV = ptx::make_sdesc_sw128(st + kKBytes, 1024, 1024);
-#pragma unroll
-              for (int k = 0; k < kBN / 16; ++k)
-                ptx::umma_bf16(tmem_base + s * 256, dP + 2 * k, dV + static_cast<uint64_t>(k) * (2048 >> 4), idesc_o,
-                               k != 0);
-              ptx::tc_commit(&o_full[s]);
-              ptx::tc_commit(&kv_empty[kvs]);
-              pv_next[s] = kt + 2;
-              --remaining;
-              progressed = true;
-            }
-          }
+          for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS + kBN + 128, dQv + 2 * k, d2 + 2 * k, idesc_g64, k != 0);
         }
-        if (progressed) {
-          t_idle = 0;
-        } else {
-          if (t_idle == 0) t_idle = clock64();
-          else if (clock64() - t_idle > CFB_MBAR_TIMEOUT_CYCLES) __trap();
+        ptx::tc_commit(&band_empty[s0]);  // block kt is not read by any later tile
+      };
+      if (s < n_kt) issue_g(s);
+      int it = 0;
+      for (int kt = s; kt < n_kt; kt += 2, ++it) {
+        const int kvs = kt % kKVStages;
+        const bool tr = (p.debug & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && s == 0 && it < 60;
+        if (tr) p.trace[512 + it * 8 + 0] = clock64();
+        // ---- S of key tile kt (its G is already in flight or done)
+        ptx::mbar_wait(&kv_full[kvs], (kt / kKVStages) & 1);
+        ptx::mbar_wait(&s_free[s], (it & 1) ^ 1);
+        ptx::tc_fence_after();
+        if (tr) p.trace[512 + it * 8 + 1] = clock64();
+        const uint32_t st = ptx::smem_u32(smem + kOffKV + kvs * kKVBytes);
+        const uint64_t dK = ptx::make_sdesc_sw128(st, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16(tS, dQu + 2 * k, dK + 2 * k, idesc_s, k != 0);
+        ptx::tc_commit(&sg_full[s]);
+        if (tr) p.trace[512 + it * 8 + 2] = clock64();
+        // ---- G of the set's next tile, once this tile's G window has been read
+        if (kt + 2 < n_kt) {
+          ptx::mbar_wait(&g_free[s], it & 1);
+          issue_g(kt + 2);
         }
+        if (tr) p.trace[512 + it * 8 + 3] = clock64();
+        // ---- O_part = P V once the set has written its probabilities
+        ptx::mbar_wait(&p_ready[s], it & 1);
+        ptx::tc_fence_after();
+        if (tr) p.trace[512 + it * 8 + 4] = clock64();
+        // V tile: 64 keys (K of this MMA) x 64 dk (N), 128-byte rows along N -> MN-major, 8-key groups 1 KB apart
+        const uint64_t dV = ptx::make_sdesc_sw128(st + kKBytes, 1024, 1024);
+#pragma unroll
+        for (int k = 0; k < kBN / 16; ++k)
+          ptx::umma_bf16(tS, dP + 2 * k, dV + static_cast<uint64_t>(k) * (2048 >> 4), idesc_o, k != 0);
+        ptx::tc_commit(&o_full[s]);
+        ptx::tc_commit(&kv_empty[kvs]);
+        if (tr) p.trace[512 + it * 8 + 5] = clock64();
       }
     }
   }
@@ -289,50 +281,86 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int kt = set; kt < n_kt; kt += 2, ++it) {
       const int j0 = kt * kBN;
       if (it > 0) {
+        const bool tr2 = (p.debug & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 4 && lane == 0 && it < 60;
         ptx::mbar_wait(&o_full[set], (it - 1) & 1);
         ptx::tc_fence_after();
+        if (tr2) p.trace[it * 8 + 5] = clock64();
         fold_o_part();
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&sg_free[set]);  // the buffer may now receive the S / G of this tile
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&s_free[set]);  // the S columns may now receive this tile's scores
+        if (tr2) p.trace[it * 8 + 6] = clock64();
       }
+      const bool tr = (p.debug & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 4 && lane == 0 && it < 60;
+      if (tr) p.trace[it * 8 + 0] = clock64();
       ptx::mbar_wait(&sg_full[set], it & 1);
       ptx::tc_fence_after();
+      if (tr) p.trace[it * 8 + 1] = clock64();
       float sv[kBN];
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {  // 32 keys at a time: window of 63 columns through the private row
-        uint32_t w0[32], w1[32], a[32];
-        ptx::tmem_ld_x32(tS + g_base + hf * 32, w0);       // all loads of this half in flight, one wait
-        ptx::tmem_ld_x32(tS + g_base + hf * 32 + 32, w1);
-        ptx::tmem_ld_x32(tS + hf * 32, a);
+      {
+        // S (64 columns) and the first half of the G window in flight together; the second half of the window is
+        // requested before the first half is consumed, so its TMEM latency hides behind the shared-memory shift.
+        uint32_t s0r[32], s1r[32], w0[32], w1[32];
+        ptx::tmem_ld_x32(tS, s0r);
+        ptx::tmem_ld_x32(tS + 32, s1r);
+        ptx::tmem_ld_x32(tS + g_base, w0);
+        ptx::tmem_ld_x32(tS + g_base + 32, w1);
         ptx::tc_wait_ld();
+        if (!(p.debug & 4)) {
 #pragma unroll
-        for (int v4 = 0; v4 < 8; ++v4) {
-          ptx::sts128(shift_row + v4 * 16, w0[4 * v4], w0[4 * v4 + 1], w0[4 * v4 + 2], w0[4 * v4 + 3]);
-          ptx::sts128(shift_row + 128 + v4 * 16, w1[4 * v4], w1[4 * v4 + 1], w1[4 * v4 + 2], w1[4 * v4 + 3]);
+          for (int v4 = 0; v4 < 8; ++v4) {
+            ptx::sts128(shift_row + v4 * 16, w0[4 * v4], w0[4 * v4 + 1], w0[4 * v4 + 2], w0[4 * v4 + 3]);
+            ptx::sts128(shift_row + 128 + v4 * 16, w1[4 * v4], w1[4 * v4 + 1], w1[4 * v4 + 2], w1[4 * v4 + 3]);
+          }
         }
+        ptx::tmem_ld_x32(tS + g_base + 64, w0);  // window of keys 32..63 = G columns g_base+32 (still in w1) .. +95
+        {
+          float g[32];
+          ptx::lds_f32x32(shift_row + sh * 4, g);
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          sv[hf * 32 + c] = (__uint_as_float(a[c]) + ptx::lds_f32(shift_row + (sh + c) * 4)) * p.scale_log2;
+          for (int c = 0; c < 32; ++c) sv[c] = (__uint_as_float(s0r[c]) + g[c]) * p.scale_log2;
+        }
+        ptx::tc_wait_ld();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&g_free[set]);  // every TMEM read of this tile's S / G has completed
+        if (!(p.debug & 4)) {
+#pragma unroll
+          for (int v4 = 0; v4 < 8; ++v4) {
+            ptx::sts128(shift_row + v4 * 16, w1[4 * v4], w1[4 * v4 + 1], w1[4 * v4 + 2], w1[4 * v4 + 3]);
+            ptx::sts128(shift_row + 128 + v4 * 16, w0[4 * v4], w0[4 * v4 + 1], w0[4 * v4 + 2], w0[4 * v4 + 3]);
+          }
+        }
+        {
+          float g[32];
+          ptx::lds_f32x32(shift_row + sh * 4, g);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) sv[32 + c] = (__uint_as_float(s1r[c]) + g[c]) * p.scale_log2;
+        }
       }
+      if (tr) p.trace[it * 8 + 2] = clock64();
       if (j0 + kBN > len) {  // only the last key tile can contain masked keys
 #pragma unroll
         for (int c = 0; c < kBN; ++c)
           if (j0 + c >= len) sv[c] = -INFINITY;
       }
-      float mx = sv[0];
+      float mx4[4] = {sv[0], sv[1], sv[2], sv[3]};  // four independent chains instead of one 64-deep one
 #pragma unroll
-      for (int c = 1; c < kBN; ++c) mx = fmaxf(mx, sv[c]);
+      for (int c = 4; c < kBN; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], sv[c]);
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx);  // finite: every tile holds at least one key j < len
       const float alpha = fast_exp2(m_run - m_new);
-      float rsum = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < kBN; ++c) {
-        sv[c] = fast_exp2(sv[c] - m_new);
-        rsum += sv[c];
+        sv[c] = (p.debug & 1) ? (sv[c] - m_new) : fast_exp2(sv[c] - m_new);
+        rs4[c & 3] += sv[c];
       }
+      const float rsum = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       l_run = fmaf(l_run, alpha, rsum);
       m_run = m_new;
       alpha_prev = alpha;
+      if (tr) p.trace[it * 8 + 3] = clock64();
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         uint4 u;
@@ -343,8 +371,9 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ptx::sts128(prow + ((c ^ (ii & 7)) << 4), u.x, u.y, u.z, u.w);  // 128-byte swizzle, K-major
       }
       ptx::fence_proxy_async_smem();
-      ptx::tc_fence_before();  // orders this thread's TMEM reads of S/G before the PV MMA that overwrites S
-      ptx::mbar_arrive(&p_ready[set]);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_ready[set]);
+      if (tr) p.trace[it * 8 + 4] = clock64();
     }
     if (it > 0) {  // drain the last tile of this set
       ptx::mbar_wait(&o_full[set], (it - 1) & 1);
@@ -366,13 +395,17 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float w0 = fast_exp2(m_run - m), w1 = fast_exp2(m1 - m);
       const float l = l_run * w0 + l1 * w1;
       const float inv = (i < len && l > 0.f) ? 1.f / l : 0.f;  // padded query rows -> zeros
+      float o1a[32], o1b[32];
+      ptx::lds_f32x32(xrow + 8, o1a);
+      ptx::lds_f32x32(xrow + 8 + 128, o1b);
       if (i < T) {
         uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(b) * T + i) * p.Dp + h * kDK);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float r[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) r[e] = (o_acc[8 * c + e] * w0 + ptx::lds_f32(xrow + 8 + 4 * (8 * c + e)) * w1) * inv;
+          for (int e = 0; e < 8; ++e)
+            r[e] = (o_acc[8 * c + e] * w0 + (c < 4 ? o1a[8 * c + e] : o1b[8 * (c - 4) + e]) * w1) * inv;
           uint4 u;
           u.x = ptx::pack_bf16x2(r[0], r[1]);
           u.y = ptx::pack_bf16x2(r[2], r[3]);
@@ -392,7 +425,15 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+long long* g_attn_trace = nullptr;
 }  // namespace
+
+// debug: copies the clock trace of the last traced launch to the host (1024 values)
+extern "C" __attribute__((visibility("default"))) int cfb_debug_attn_trace(long long* host_out) {
+  if (!g_attn_trace) return 1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(host_out, g_attn_trace, 1024 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+}
 
 int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
   if (a.B <= 0 || a.T <= 0) return 0;
@@ -435,6 +476,20 @@ int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
   p.T = a.T;
   p.Dp = Dp;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(a.dk));
+  {
+    const char* dbg = getenv("CFB_ATTN_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+    p.trace = nullptr;
+    if (p.debug & 8) {
+      static long long* trace_buf = nullptr;
+      if (!trace_buf) {
+        cudaMalloc(&trace_buf, 1024 * sizeof(long long));
+        cudaMemset(trace_buf, 0, 1024 * sizeof(long long));
+      }
+      p.trace = trace_buf;
+      g_attn_trace = trace_buf;
+    }
+  }
   dim3 grid((a.T + kBM - 1) / kBM, a.H, a.B);
   rel_attn_tc_kernel<<<grid, kThreads, kSmemTotal, st>>>(tmQ, tmKV, tmP, p);
   cudaError_t e = cudaGetLastError();

@@ -117,10 +117,11 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   return d;
 }
 
-template <typename T, bool kFast>
+template <typename T, bool kFast, int KS>  // KS > 0: compile-time tap count (31 in every shipped recipe); 0: runtime
 __global__ void __launch_bounds__(256) depthwise_kernel(const T* __restrict__ x, const float* __restrict__ taps,
                                                         const float* __restrict__ bias, T* __restrict__ out, int T_len,
-                                                        int d, int ksize) {
+                                                        int d, int ksize_rt) {
+  const int ksize = KS > 0 ? KS : ksize_rt;
   constexpr int kRows = kDwT + kDwMaxK - 1;
   constexpr int kVec = 16 / sizeof(T);       // elements per 16-byte chunk
   constexpr int kChunks = kDwC / kVec;       // chunks per tile row
@@ -133,8 +134,9 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const T* __restrict__ x,
   const T* xb = x + static_cast<long long>(b) * T_len * d;
   T* ob = out + static_cast<long long>(b) * T_len * d;
   const int span = kDwT + ksize - 1;
+  static_assert((kChunks & (kChunks - 1)) == 0, "chunks per row must be a power of two");
   for (int i = threadIdx.x; i < span * kChunks; i += 256) {
-    const int r = i / kChunks, ch = i % kChunks;
+    const int r = i / kChunks, ch = i & (kChunks - 1);
     const int t = t0 - half + r, c = c0 + ch * kVec;
     T* dst = &tile[r][ch * kVec];
     if (t >= 0 && t < T_len && c + kVec <= d) {
@@ -356,12 +358,17 @@ int launch_depthwise(const void* x, const float* taps, const float* bias, void* 
   if (B <= 0 || T <= 0) return 0;
   if (ksize > kDwMaxK || (ksize & 1) == 0 || d % 2 != 0) return -1;
   dim3 grid(B * ((T + kDwT - 1) / kDwT), (d + kDwC - 1) / kDwC);
-  if (is_bf16)
-    depthwise_kernel<bf16, true><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), taps, bias,
-                                                       reinterpret_cast<bf16*>(out), T, d, ksize);
-  else
-    depthwise_kernel<float, false><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), taps, bias,
-                                                         reinterpret_cast<float*>(out), T, d, ksize);
+  if (is_bf16) {
+    if (ksize == 31)
+      depthwise_kernel<bf16, true, 31><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), taps, bias,
+                                                             reinterpret_cast<bf16*>(out), T, d, ksize);
+    else
+      depthwise_kernel<bf16, true, 0><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), taps, bias,
+                                                            reinterpret_cast<bf16*>(out), T, d, ksize);
+  } else {
+    depthwise_kernel<float, false, 0><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), taps, bias,
+                                                            reinterpret_cast<float*>(out), T, d, ksize);
+  }
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -225,6 +225,47 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
+// 32 consecutive words from shared memory in ONE asm statement, so the loads issue back to back (32 separate
+// volatile statements would each be followed by their dependent math and serialise on the ~30-cycle LDS latency)
+__device__ __forceinline__ void lds_f32x32(uint32_t addr, float (&v)[32]) {
+  asm volatile(
+      "ld.shared.f32 %0, [%32+0];\n"
+      "ld.shared.f32 %1, [%32+4];\n"
+      "ld.shared.f32 %2, [%32+8];\n"
+      "ld.shared.f32 %3, [%32+12];\n"
+      "ld.shared.f32 %4, [%32+16];\n"
+      "ld.shared.f32 %5, [%32+20];\n"
+      "ld.shared.f32 %6, [%32+24];\n"
+      "ld.shared.f32 %7, [%32+28];\n"
+      "ld.shared.f32 %8, [%32+32];\n"
+      "ld.shared.f32 %9, [%32+36];\n"
+      "ld.shared.f32 %10, [%32+40];\n"
+      "ld.shared.f32 %11, [%32+44];\n"
+      "ld.shared.f32 %12, [%32+48];\n"
+      "ld.shared.f32 %13, [%32+52];\n"
+      "ld.shared.f32 %14, [%32+56];\n"
+      "ld.shared.f32 %15, [%32+60];\n"
+      "ld.shared.f32 %16, [%32+64];\n"
+      "ld.shared.f32 %17, [%32+68];\n"
+      "ld.shared.f32 %18, [%32+72];\n"
+      "ld.shared.f32 %19, [%32+76];\n"
+      "ld.shared.f32 %20, [%32+80];\n"
+      "ld.shared.f32 %21, [%32+84];\n"
+      "ld.shared.f32 %22, [%32+88];\n"
+      "ld.shared.f32 %23, [%32+92];\n"
+      "ld.shared.f32 %24, [%32+96];\n"
+      "ld.shared.f32 %25, [%32+100];\n"
+      "ld.shared.f32 %26, [%32+104];\n"
+      "ld.shared.f32 %27, [%32+108];\n"
+      "ld.shared.f32 %28, [%32+112];\n"
+      "ld.shared.f32 %29, [%32+116];\n"
+      "ld.shared.f32 %30, [%32+120];\n"
+      "ld.shared.f32 %31, [%32+124];\n"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(addr)
+      : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
