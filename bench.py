@@ -256,6 +256,24 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = audio_sec * world / (ms_step / 1e3)
 
+    # ---------------- same forward replayed from a CUDA graph (cfb_forward is enqueue-only, hence capturable)
+    graph_ms = None
+    try:
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            yg, lg = enc(audio_signal=x_dev, length=len_dev)
+        for _ in range(3):
+            gph.replay()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            gph.replay()
+        e1.record()
+        barrier()
+        graph_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    except Exception as exc:  # pragma: no cover
+        graph_ms = f"failed: {exc!r}"
+
     # ---------------- end to end through the public API with host buffers
     # Every step copies its features host->device from pinned memory, calls ConformerEncoder.forward, and copies
     # (encoded, encoded_len) device->host -- all inside the timed region, on one stream.  (A three-stream
@@ -334,7 +352,8 @@ def run_b200(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (randn log-mel features, random-init weights)",
         "config": workload_config(args.workload, world), "clocks": clocks, "e2e": e2e,
-        "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "kernels": kernels,
+        "gpu_launches": launches_per_step * args.steps, "cuda_graph_ms_per_step": graph_ms, "roofline": roofline,
+        "kernels": kernels,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
