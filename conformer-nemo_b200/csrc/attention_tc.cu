@@ -36,15 +36,18 @@ namespace {
 constexpr int kBM = 128;   // queries per CTA
 constexpr int kBN = 64;    // keys per tile
 constexpr int kDK = 64;    // padded head dim
-constexpr int kThreads = 384;  // warpgroup 0: TMA + MMA issuers; warpgroups 1, 2: softmax sets 0, 1
+constexpr int kThreads = 384;  // warpgroup 0: TMA + MMA issuers; warpgroups 1, 2: softmax sets 0, 1.  (The SMSP arbiter
+                               // favours high warp ids: issuers placed ABOVE the softmax warps were measured to
+                               // steal issue slots with their mbarrier polling, +15 % kernel time.)
 constexpr int kKBytes = kBN * kDK * 2;     // 8 KB
-constexpr int kKVStages = 4;               // K + V tiles, 16 KB per stage
+constexpr int kKVStages = 3;               // K + V tiles, 16 KB per stage
 constexpr int kKVBytes = 2 * kKBytes;
 constexpr int kBandSlots = 3;              // 64-row band blocks in flight (each is consumed by exactly one MMA)
 constexpr int kBlockBytes = 64 * kDK * 2;
 constexpr int kGSlots = 4;                 // TMEM ring of G blocks
-constexpr int kShiftQuads = 400;           // per softmax warp: 32 rows of 12 quads (96 fp16) at staggered starts
-constexpr int kShiftBytes = kShiftQuads * 16;
+constexpr int kShiftPitch = 100;           // words per private shift row (96-column fp32 window + pad): 16-byte
+                                           // stores and 4-byte loads at word offset (31 - lane) are conflict-free
+constexpr int kShiftBytes = 32 * kShiftPitch * 4;
 constexpr int kXPitch = 68;                // words per row of the end-of-kernel set exchange (m, l, O[64])
 constexpr int kOffKV = 0;
 constexpr int kOffBand = kOffKV + kKVStages * kKVBytes;
@@ -61,6 +64,8 @@ struct AttnParams {
   bf16* ctx;
   int T, Dp;
   float scale_log2;  // log2(e) / sqrt(dk)
+  int debug;         // CFB_ATTN_DEBUG ablation bits (timing experiments only; results are wrong when non-zero)
+  long long* trace;  // CFB_ATTN_TRACE=1: clock64 trace of CTA (0,0,0) (timing experiments only)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -77,12 +82,18 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
   return d;
 }
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
 
+template <bool kInstr>  // kInstr: clock trace + ablation switches (timing experiments only)
 __global__ void __launch_bounds__(kThreads, 1)
 rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmP,
                    const AttnParams p) {
@@ -91,8 +102,14 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   const int b = blockIdx.z;
   const int T = p.T;
   const int len = min(p.lens[b], T);
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
+  uint32_t tid;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));  // volatile: keeps warp / lane in registers (no S2R re-reads)
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const bool trc = kInstr && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  const int dbg = kInstr ? p.debug : 0;
+#define CFB_TR(slot) do { if (kInstr && trc) p.trace[slot] = clock64(); } while (0)
+  if (warp == 4) CFB_TR(0);
 
   if (i0 >= len) {
     // the whole query tile is padding: context is zero (block-uniform exit, nothing allocated yet)
@@ -108,137 +125,208 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   }
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* q_ready = bars + 0;   // both Q operands are in TMEM (8 warp arrivals)
-  uint64_t* sg_full = bars + 1;   // [2] per set: S of the set's current key tile is in TMEM
-  uint64_t* s_free = bars + 3;    // [2] O_part folded: the S columns may be overwritten
-  uint64_t* g_free = bars + 5;    // [2] per set: the G window of the set's tile has been read out of the ring
-  uint64_t* p_ready = bars + 7;   // [2]
-  uint64_t* o_full = bars + 9;    // [2]
-  uint64_t* kv_full = bars + 11;                   // [kKVStages]
-  uint64_t* kv_empty = kv_full + kKVStages;        // [kKVStages]
-  uint64_t* band_full = kv_empty + kKVStages;      // [kBandSlots]
-  uint64_t* band_empty = band_full + kBandSlots;   // [kBandSlots]
-  uint64_t* g_full = band_empty + kBandSlots;      // [kGSlots] G block in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + kGSlots);
+  // every shared-memory object is addressed through a 32-bit shared address derived once from this base
+  const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = sbase + kOffBar;
+  const uint32_t qu_ready = bar0 + 0;    // Q+u is in TMEM (4 warp arrivals, softmax set 0)
+  const uint32_t qv_ready = bar0 + 8;    // Q+v is in TMEM (4 warp arrivals, softmax set 1)
+  const uint32_t sg_full = bar0 + 16;    // [2] per set: S of the set's current key tile is in TMEM
+  const uint32_t s_free = bar0 + 32;     // [2] O_part folded: the S columns may be overwritten
+  const uint32_t g_free = bar0 + 48;     // [2] per set: the G window of the set's tile has been read out of the ring
+  const uint32_t p_ready = bar0 + 64;    // [2]
+  const uint32_t o_full = bar0 + 80;     // [2]
+  const uint32_t exp_done = bar0 + 96;   // [2] per set: the exponentials of the set's tile have issued
+  const uint32_t kv_full = bar0 + 112;                   // [kKVStages]
+  const uint32_t kv_empty = kv_full + 8 * kKVStages;     // [kKVStages]
+  const uint32_t band_full = kv_empty + 8 * kKVStages;   // [kBandSlots]
+  const uint32_t band_empty = band_full + 8 * kBandSlots;  // [kBandSlots]
+  const uint32_t g_full = band_empty + 8 * kBandSlots;   // [kGSlots] G block in TMEM
+  const uint32_t tmem_slot = g_full + 8 * kGSlots;
+  static_assert(112 + 8 * (2 * kKVStages + 2 * kBandSlots + kGSlots) + 8 <= 256, "barrier area");
 
   const int n_kt = (len + kBN - 1) / kBN;
   const int n_gb = n_kt + 2;  // G blocks 0 .. n_kt+1
+
+  uint32_t qw[32];  // softmax warps: this thread's row of Q+u (set 0) / Q+v (set 1), 64 bf16, fetched before the setup
+  if (warp >= 4) {
+    const int i = i0 + (warp & 3) * 32 + lane;
+    if (i < T) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<long long>(b) * T + i) * (4 * p.Dp) +
+                                                        ((warp - 4) >> 2) * p.Dp + h * kDK);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = __ldg(src + c);
+        qw[4 * c] = u.x, qw[4 * c + 1] = u.y, qw[4 * c + 2] = u.z, qw[4 * c + 3] = u.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) qw[c] = 0u;
+    }
+  }
 
   if (warp == 0) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmKV);
       ptx::prefetch_tmap(&tmP);
-      ptx::mbar_init(q_ready, 8);
+      ptx::mbar_init_a(qu_ready, 4);
+      ptx::mbar_init_a(qv_ready, 4);
       for (int s = 0; s < kKVStages; ++s) {
-        ptx::mbar_init(&kv_full[s], 1);
-        ptx::mbar_init(&kv_empty[s], 1);
+        ptx::mbar_init_a(kv_full + 8 * s, 1);
+        ptx::mbar_init_a(kv_empty + 8 * s, 1);
       }
       for (int s = 0; s < kBandSlots; ++s) {
-        ptx::mbar_init(&band_full[s], 1);
-        ptx::mbar_init(&band_empty[s], 1);
+        ptx::mbar_init_a(band_full + 8 * s, 1);
+        ptx::mbar_init_a(band_empty + 8 * s, 1);
       }
-      for (int s = 0; s < kGSlots; ++s) ptx::mbar_init(&g_full[s], 1);
+      for (int s = 0; s < kGSlots; ++s) ptx::mbar_init_a(g_full + 8 * s, 1);
       for (int s = 0; s < 2; ++s) {
-        ptx::mbar_init(&sg_full[s], 1);
-        ptx::mbar_init(&s_free[s], 4);   // one elected arrival per softmax warp
-        ptx::mbar_init(&g_free[s], 4);
-        ptx::mbar_init(&p_ready[s], 4);
-        ptx::mbar_init(&o_full[s], 1);
+        ptx::mbar_init_a(sg_full + 8 * s, 1);
+        ptx::mbar_init_a(s_free + 8 * s, 4);   // one elected arrival per softmax warp
+        ptx::mbar_init_a(g_free + 8 * s, 4);
+        ptx::mbar_init_a(p_ready + 8 * s, 4);
+        ptx::mbar_init_a(o_full + 8 * s, 1);
+        ptx::mbar_init_a(exp_done + 8 * s, 4);
       }
       ptx::fence_mbar_init();
+      // the first loads only need their own barriers: issue them before the CTA-wide setup barrier
+      const int r0 = T - 1 - i0 - (kBM - 1);  // band row of G column 0 of block 0 (may be < 0: TMA zero-fills)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        ptx::mbar_arrive_expect_tx_a(band_full + 8 * g, kBlockBytes);
+        ptx::tma_load_2d_a(sbase + kOffBand + g * kBlockBytes, &tmP, band_full + 8 * g, h * kDK, r0 + 64 * g);
+      }
+      ptx::mbar_arrive_expect_tx_a(kv_full, kKVBytes);
+      ptx::tma_load_2d_a(sbase + kOffKV, &tmKV, kv_full, 2 * p.Dp + h * kDK, b * T);
+      ptx::tma_load_2d_a(sbase + kOffKV + kKBytes, &tmKV, kv_full, 3 * p.Dp + h * kDK, b * T);
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  if (warp == 4) CFB_TR(1);
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
     if (warp == 0) {
       // ---------------------------------------------------------------------------------- TMA producer
       if (lane == 0) {
-        const int r0 = T - 1 - i0 - (kBM - 1);  // band row of G column 0 of block 0 (may be < 0: TMA zero-fills)
+        const int r0 = T - 1 - i0 - (kBM - 1);
         auto load_band_block = [&](int g) {
           if (g >= n_gb) return;
           const int slot = g % kBandSlots, use = g / kBandSlots;
-          ptx::mbar_wait(&band_empty[slot], (use & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&band_full[slot], kBlockBytes);
-          ptx::tma_load_2d(smem + kOffBand + slot * kBlockBytes, &tmP, &band_full[slot], h * kDK, r0 + 64 * g);
+          ptx::mbar_wait_a(band_empty + 8 * slot, (use & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx_a(band_full + 8 * slot, kBlockBytes);
+          ptx::tma_load_2d_a(sbase + kOffBand + slot * kBlockBytes, &tmP, band_full + 8 * slot, h * kDK, r0 + 64 * g);
         };
-        load_band_block(0);
-        load_band_block(1);
-        load_band_block(2);
-        for (int kt = 0; kt < n_kt; ++kt) {
+        load_band_block(3);
+        for (int kt = 1; kt < n_kt; ++kt) {
           const int st = kt % kKVStages, use = kt / kKVStages;
-          ptx::mbar_wait(&kv_empty[st], (use & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&kv_full[st], kKVBytes);
-          uint8_t* dst = smem + kOffKV + st * kKVBytes;
-          ptx::tma_load_2d(dst, &tmKV, &kv_full[st], 2 * p.Dp + h * kDK, b * T + kt * kBN);
-          ptx::tma_load_2d(dst + kKBytes, &tmKV, &kv_full[st], 3 * p.Dp + h * kDK, b * T + kt * kBN);
+          ptx::mbar_wait_a(kv_empty + 8 * st, (use & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx_a(kv_full + 8 * st, kKVBytes);
+          const uint32_t dst = sbase + kOffKV + st * kKVBytes;
+          ptx::tma_load_2d_a(dst, &tmKV, kv_full + 8 * st, 2 * p.Dp + h * kDK, b * T + kt * kBN);
+          ptx::tma_load_2d_a(dst + kKBytes, &tmKV, kv_full + 8 * st, 3 * p.Dp + h * kDK, b * T + kt * kBN);
           load_band_block(kt + 3);
         }
       }
     } else if (warp == 1 || warp == 2) {
       // ---------------------------------------------------------------------------------- S / PV issuer of a set
-      if (lane == 0) {
-        const int s = warp - 1;
-        constexpr uint32_t idesc_s = ptx::make_idesc_bf16(kBM, kBN, 0, 0);
-        constexpr uint32_t idesc_o = ptx::make_idesc_bf16(kBM, kDK, 0, 1);  // B = V is MN-major (keys x dk rows)
-        const uint32_t tQu = tmem_base + kColQ;
-        const uint32_t tS = tmem_base + kColS + s * 64;
-        const uint32_t tP = tmem_base + kColP + s * 32;
-        ptx::mbar_wait(q_ready, 0);
+      // Warp-uniform control flow (all lanes wait, one elected lane issues): addresses and descriptors stay in
+      // uniform registers, which keeps the wait -> first-MMA latency on the softmax critical path short.
+      const int s = warp - 1;
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(kBM, kBN, 0, 0);
+      constexpr uint32_t idesc_o = ptx::make_idesc_bf16(kBM, kDK, 0, 1);  // B = V is MN-major (keys x dk rows)
+      const uint32_t tQu = tmem_base + kColQ;
+      const uint32_t tS = tmem_base + kColS + s * 64;
+      const uint32_t tP = tmem_base + kColP + s * 32;
+      ptx::mbar_wait_a(qu_ready, 0);
+      ptx::tc_fence_after();
+      int it = 0;
+      for (int kt = s; kt < n_kt; kt += 2, ++it) {
+        const int kvs = kt % kKVStages;
+        const bool ti = kInstr && s == 0 && it < 30;
+        const uint32_t st = sbase + kOffKV + kvs * kKVBytes;
+        const uint64_t dK = ptx::make_sdesc_sw128(st, 16, 1024);
+        // V tile: 64 keys (K of this MMA) x 64 dk (N), 128-byte rows along N -> MN-major, 8-key groups 1 KB apart
+        const uint64_t dV = ptx::make_sdesc_sw128(st + kKBytes, 1024, 1024);
+        if (ti) CFB_TR(512 + it * 8 + 0);
+        ptx::mbar_wait_a(kv_full + 8 * kvs, (kt / kKVStages) & 1);
+        if (ti) CFB_TR(512 + it * 8 + 1);
+        ptx::mbar_wait_a(s_free + 8 * s, (it & 1) ^ 1);
         ptx::tc_fence_after();
-        int it = 0;
-        for (int kt = s; kt < n_kt; kt += 2, ++it) {
-          const int kvs = kt % kKVStages;
-          ptx::mbar_wait(&kv_full[kvs], (kt / kKVStages) & 1);
-          ptx::mbar_wait(&s_free[s], (it & 1) ^ 1);
-          ptx::tc_fence_after();
-          const uint32_t st = ptx::smem_u32(smem + kOffKV + kvs * kKVBytes);
-          const uint64_t dK = ptx::make_sdesc_sw128(st, 16, 1024);
+        if (ti) CFB_TR(512 + it * 8 + 2);
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16_ts(tS, tQu + 8 * k, dK + 2 * k, idesc_s, k != 0);
-          ptx::tc_commit(&sg_full[s]);
-          // ---- O_part = P V once the set has stored its probabilities (P is a TMEM A operand: 8 columns per K=16)
-          ptx::mbar_wait(&p_ready[s], it & 1);
-          ptx::tc_fence_after();
-          // V tile: 64 keys (K of this MMA) x 64 dk (N), 128-byte rows along N -> MN-major, 8-key groups 1 KB apart
-          const uint64_t dV = ptx::make_sdesc_sw128(st + kKBytes, 1024, 1024);
+          ptx::tc_commit_a(sg_full + 8 * s);
+        }
+        __syncwarp();
+        if (ti) CFB_TR(512 + it * 8 + 3);
+        // ---- O_part = P V once the set has stored its probabilities (P is a TMEM A operand: 8 columns per K=16)
+        ptx::mbar_wait_a(p_ready + 8 * s, it & 1);
+        ptx::tc_fence_after();
+        if (ti) CFB_TR(512 + it * 8 + 4);
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < kBN / 16; ++k)
             ptx::umma_bf16_ts(tS, tP + 8 * k, dV + static_cast<uint64_t>(k) * (2048 >> 4), idesc_o, k != 0);
-          ptx::tc_commit(&o_full[s]);
-          ptx::tc_commit(&kv_empty[kvs]);
+          ptx::tc_commit_a(o_full + 8 * s);
+          ptx::tc_commit_a(kv_empty + 8 * kvs);
         }
+        __syncwarp();
+        if (ti) CFB_TR(512 + it * 8 + 5);
       }
     } else {
       // ---------------------------------------------------------------------------------- G ring issuer
-      if (lane == 0) {
-        constexpr uint32_t idesc_g = ptx::make_idesc_bf16(kBM, 64, 0, 0);
-        const uint32_t tQv = tmem_base + kColQ + 32;
-        const uint32_t band_base = ptx::smem_u32(smem + kOffBand);
-        ptx::mbar_wait(q_ready, 0);
-        for (int g = 0; g < n_gb; ++g) {
-          const int bs = g % kBandSlots;
-          ptx::mbar_wait(&band_full[bs], (g / kBandSlots) & 1);
-          // ring slot g%4 held block g-4, read by key tiles g-6, g-5, g-4.  Tile g-5 (the other set's) was waited
-          // for at step g-1 and tile g-6 precedes g-4 in its set, so one wait per step covers all three readers
-          // (waiting again for g-5 here could alias: that set may already be two phases further).
-          if (g >= 4 && g - 4 < n_kt) ptx::mbar_wait(&g_free[(g - 4) & 1], ((g - 4) >> 1) & 1);
-          ptx::tc_fence_after();
-          const uint64_t dB = ptx::make_sdesc_sw128(band_base + bs * kBlockBytes, 16, 1024);
-          const uint32_t tG = tmem_base + kColG + (g % kGSlots) * 64;
+      constexpr uint32_t idesc_g = ptx::make_idesc_bf16(kBM, 64, 0, 0);
+      constexpr uint32_t idesc_g3 = ptx::make_idesc_bf16(kBM, 192, 0, 0);
+      const uint32_t tQv = tmem_base + kColQ + 32;
+      const uint32_t band_base = sbase + kOffBand;
+      ptx::mbar_wait_a(qv_ready, 0);
+      // blocks 0..2 sit in consecutive band slots and ring slots: one 192-wide MMA group
+      ptx::mbar_wait_a(band_full + 0, 0);
+      ptx::mbar_wait_a(band_full + 8, 0);
+      ptx::mbar_wait_a(band_full + 16, 0);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint64_t dB = ptx::make_sdesc_sw128(band_base, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kDK / 16; ++k)
+          ptx::umma_bf16_ts(tmem_base + kColG, tQv + 8 * k, dB + 2 * k, idesc_g3, k != 0);
+        ptx::tc_commit_a(g_full + 0);  // every ring slot's barrier advances one phase per block it receives
+        ptx::tc_commit_a(g_full + 8);
+        ptx::tc_commit_a(g_full + 16);
+        ptx::tc_commit_a(band_empty + 0);
+        ptx::tc_commit_a(band_empty + 8);
+        ptx::tc_commit_a(band_empty + 16);
+      }
+      __syncwarp();
+      CFB_TR(800 + 2);
+      for (int g = 3; g < n_gb; ++g) {
+        const int bs = g % kBandSlots;
+        const uint64_t dB = ptx::make_sdesc_sw128(band_base + bs * kBlockBytes, 16, 1024);
+        const uint32_t tG = tmem_base + kColG + (g % kGSlots) * 64;
+        ptx::mbar_wait_a(band_full + 8 * bs, (g / kBandSlots) & 1);
+        // ring slot g%4 held block g-4, read by key tiles g-6, g-5, g-4.  Tile g-5 (the other set's) was waited
+        // for at step g-1 and tile g-6 precedes g-4 in its set, so one wait per step covers all three readers
+        // (waiting again for g-5 here could alias: that set may already be two phases further).
+        if (g >= 4 && g - 4 < n_kt) ptx::mbar_wait_a(g_free + 8 * ((g - 4) & 1), ((g - 4) >> 1) & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < kDK / 16; ++k) ptx::umma_bf16_ts(tG, tQv + 8 * k, dB + 2 * k, idesc_g, k != 0);
-          ptx::tc_commit(&g_full[g % kGSlots]);
-          ptx::tc_commit(&band_empty[bs]);
+          ptx::tc_commit_a(g_full + 8 * (g % kGSlots));
+          ptx::tc_commit_a(band_empty + 8 * bs);
         }
+        __syncwarp();
+        if (g < 30) CFB_TR(800 + g);
       }
     }
   } else {
@@ -253,61 +341,46 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
     const uint32_t tP = t_lane + kColP + set * 32;
 
     // ---- this thread's row of Q+u (set 0) or Q+v (set 1) -> TMEM A operand
-    {
-      uint32_t qw[32];
-      if (i < T) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<long long>(b) * T + i) * (4 * p.Dp) +
-                                                          set * p.Dp + h * kDK);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 u = __ldg(src + c);
-          qw[4 * c] = u.x, qw[4 * c + 1] = u.y, qw[4 * c + 2] = u.z, qw[4 * c + 3] = u.w;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) qw[c] = 0u;
-      }
-      ptx::tmem_st_x32(t_lane + kColQ + set * 32, qw);
-      ptx::tc_wait_st();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(q_ready);
-    }
+    ptx::tmem_st_x32(t_lane + kColQ + set * 32, qw);
+    ptx::tc_wait_st();
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive_a(set == 0 ? qu_ready : qv_ready);
+    if (warp == 4) CFB_TR(2);
 
     // rel_shift: row ii needs window column (31 - lane) + jj of the 96 columns starting at ring column
-    // 64 kt + 96 - 32 quarter.  The window is stored as fp16 pairs in a private row whose start (in 16-byte quads)
-    // is staggered so that both the 16-byte stores and the 4-byte loads at word offset (31 - lane) / 2 hit 32 banks.
+    // 64 kt + 96 - 32 quarter.  The window goes through a private fp32 shared-memory row: stored with 16-byte
+    // stores while the P V MMA of the previous tile runs, read back at word offset 31 - lane when S arrives.
     const int sh = 31 - lane;
-    const uint32_t sel = (sh & 1) ? 0x5432u : 0x3210u;  // odd shift: word k = (half 2k+1, half 2k+2)
-    const uint32_t shift_row = ptx::smem_u32(smem + kOffShift + (warp - 4) * kShiftBytes) +
-                               (12 * lane + ((lane >> 1) & 3) + 4 * (lane >> 3)) * 16;
+    const uint32_t shift_row = sbase + kOffShift + (warp - 4) * kShiftBytes + lane * kShiftPitch * 4;
     const int wcol = 96 - 32 * quarter;  // window start inside the concatenation of ring blocks kt, kt+1, kt+2
-    uint32_t gp[32];                      // shifted G of the next tile to process: (jj = 2m, 2m+1) as fp16 pairs
 
-    auto fetch_window = [&](int kt) {
-      ptx::mbar_wait(&g_full[(kt + 2) % kGSlots], ((kt + 2) / kGSlots) & 1);  // blocks complete in order
+    auto fetch_window = [&](int kt, int tslot) {
+      ptx::mbar_wait_a(g_full + 8 * ((kt + 2) % kGSlots), ((kt + 2) / kGSlots) & 1);  // blocks complete in order
       ptx::tc_fence_after();
+      if (tslot) CFB_TR(tslot);
       uint32_t w[96];
+      if (dbg & 32) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int wc = wcol + 32 * c;
-        const int blk = kt + (wc >> 6);
-        ptx::tmem_ld_x32(t_lane + kColG + (blk % kGSlots) * 64 + (wc & 63), *reinterpret_cast<uint32_t(*)[32]>(&w[32 * c]));
+        for (int c = 0; c < 96; ++c) w[c] = 0u;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int wc = wcol + 32 * c;
+          const int blk = kt + (wc >> 6);
+          ptx::tmem_ld_x32(t_lane + kColG + (blk % kGSlots) * 64 + (wc & 63),
+                           *reinterpret_cast<uint32_t(*)[32]>(&w[32 * c]));
+        }
+        ptx::tc_wait_ld();
       }
-      ptx::tc_wait_ld();
+      if (tslot) CFB_TR(tslot + 1);
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&g_free[set]);
-      uint32_t a[48];
+      if (lane == 0) ptx::mbar_arrive_a(g_free + 8 * set);
+      if (!(dbg & 2)) {
 #pragma unroll
-      for (int k = 0; k < 48; ++k) a[k] = pack_f16x2(__uint_as_float(w[2 * k]), __uint_as_float(w[2 * k + 1]));
-#pragma unroll
-      for (int k = 0; k < 47; ++k) a[k] = prmt(a[k], a[k + 1], sel);
-#pragma unroll
-      for (int q = 0; q < 12; ++q) ptx::sts128(shift_row + q * 16, a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-      const uint32_t rd = shift_row + (sh >> 1) * 4;
-#pragma unroll
-      for (int m = 0; m < 32; ++m) gp[m] = lds_u32(rd + 4 * m);
+        for (int q = 0; q < 24; ++q) ptx::sts128(shift_row + q * 16, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+      }
     };
 
     float o_acc[kDK];
@@ -316,33 +389,47 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
     float m_run = -INFINITY, l_run = 0.f;
     const float scale = p.scale_log2;
 
-    if (set < n_kt) fetch_window(set);
+    if (set < n_kt) fetch_window(set, 0);
+    if (warp == 4) CFB_TR(3);
     int it = 0;
     for (int kt = set; kt < n_kt; kt += 2, ++it) {
       const int j0 = kt * kBN;
-      ptx::mbar_wait(&sg_full[set], it & 1);
+      const bool ts = kInstr && warp == 4 && it < 30;
+      if (ts) CFB_TR(16 + it * 16 + 0);
+      ptx::mbar_wait_a(sg_full + 8 * set, it & 1);
       ptx::tc_fence_after();
+      if (ts) CFB_TR(16 + it * 16 + 1);
       float sv[kBN];
       {
         uint32_t s0r[32], s1r[32];
         ptx::tmem_ld_x32(tS, s0r);
         ptx::tmem_ld_x32(tS + 32, s1r);
         ptx::tc_wait_ld();
+        if (ts) CFB_TR(16 + it * 16 + 10);
+        float g[32];
+        if (dbg & 4) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&gp[m]));
-          const float2 g1 = __half22float2(*reinterpret_cast<const __half2*>(&gp[16 + m]));
-          sv[2 * m] = __uint_as_float(s0r[2 * m]) + g0.x;
-          sv[2 * m + 1] = __uint_as_float(s0r[2 * m + 1]) + g0.y;
-          sv[32 + 2 * m] = __uint_as_float(s1r[2 * m]) + g1.x;
-          sv[32 + 2 * m + 1] = __uint_as_float(s1r[2 * m + 1]) + g1.y;
+          for (int c = 0; c < 32; ++c) g[c] = 0.f;
+        } else {
+          ptx::lds_f32x32(shift_row + sh * 4, g);
         }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) sv[c] = __uint_as_float(s0r[c]) + g[c];
+        if (!(dbg & 4)) ptx::lds_f32x32(shift_row + sh * 4 + 128, g);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) sv[32 + c] = __uint_as_float(s1r[c]) + g[c];
       }
+      if (ts) CFB_TR(16 + it * 16 + 2);
       if (j0 + kBN > len) {  // only the last key tile can contain masked keys
 #pragma unroll
         for (int c = 0; c < kBN; ++c)
           if (j0 + c >= len) sv[c] = -INFINITY;
       }
+      // The exponentials of consecutive key tiles take turns on the MUFU pipe (tile kt after tile kt-1): the two
+      // sets then stay in anti-phase, one in its MUFU phase while the other is in its shared-memory / TMEM phases,
+      // instead of drifting into lock-step and halving each other's throughput in every phase.
+      if (kt > 0 && !(dbg & 8)) ptx::mbar_wait_a(exp_done + 8 * (set ^ 1), (set == 0 ? it - 1 : it) & 1);
+      if (ts) CFB_TR(16 + it * 16 + 11);
       float mx4[4] = {sv[0], sv[1], sv[2], sv[3]};  // four independent chains instead of one 64-deep one
 #pragma unroll
       for (int c = 4; c < kBN; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], sv[c]);
@@ -354,11 +441,16 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       uint32_t pw[32];
 #pragma unroll
       for (int m = 0; m < 32; ++m) {
-        const float e0 = fast_exp2(fmaf(sv[2 * m], scale, -ms));
-        const float e1 = fast_exp2(fmaf(sv[2 * m + 1], scale, -ms));
+        const float a0 = fmaf(sv[2 * m], scale, -ms), a1 = fmaf(sv[2 * m + 1], scale, -ms);
+        const float e0 = (dbg & 1) ? a0 : fast_exp2(a0);
+        const float e1 = (dbg & 1) ? a1 : fast_exp2(a1);
         rs4[m & 3] += e0 + e1;
-        pw[m] = ptx::pack_bf16x2(e0, e1);
+        // bf16 pair without the conversion unit (it shares the MUFU pipe): round half up with integer adds, one PRMT
+        pw[m] = prmt(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632u);
       }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_a(exp_done + 8 * set);
+      if (ts) CFB_TR(16 + it * 16 + 3);
       ptx::tmem_st_x32(tP, pw);
       const float rsum = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       l_run = fmaf(l_run, alpha, rsum);
@@ -366,17 +458,25 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       ptx::tc_wait_st();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&p_ready[set]);
+      if (lane == 0) ptx::mbar_arrive_a(p_ready + 8 * set);
+      if (ts) CFB_TR(16 + it * 16 + 4);
       // ---- the G window of this set's next tile, while the P V MMA runs
-      if (kt + 2 < n_kt) fetch_window(kt + 2);
+      if (kt + 2 < n_kt) fetch_window(kt + 2, ts ? 16 + it * 16 + 8 : 0);
+      if (ts) CFB_TR(16 + it * 16 + 5);
       // ---- o_acc = o_acc * alpha + O_part (the S columns of this set)
-      ptx::mbar_wait(&o_full[set], it & 1);
+      ptx::mbar_wait_a(o_full + 8 * set, it & 1);
       ptx::tc_fence_after();
+      if (ts) CFB_TR(16 + it * 16 + 6);
       {
         uint32_t a0[32], a1[32];
-        ptx::tmem_ld_x32(tS, a0);
-        ptx::tmem_ld_x32(tS + 32, a1);
-        ptx::tc_wait_ld();
+        if (dbg & 16) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) a0[c] = a1[c] = 0u;
+        } else {
+          ptx::tmem_ld_x32(tS, a0);
+          ptx::tmem_ld_x32(tS + 32, a1);
+          ptx::tc_wait_ld();
+        }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           o_acc[c] = fmaf(o_acc[c], alpha, __uint_as_float(a0[c]));
@@ -385,16 +485,18 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s_free[set]);  // the S columns may now receive the next tile's scores
+      if (lane == 0) ptx::mbar_arrive_a(s_free + 8 * set);  // the S columns may now receive the next tile's scores
+      if (ts) CFB_TR(16 + it * 16 + 7);
     }
 
     // ---- merge the two sets (log-sum-exp) and write the context rows.  Every MMA of the CTA has completed once
-    // both sets are past their last o_full wait, so the K/V ring can carry the exchange.
+    // both sets are past their last o_full wait, so the K/V ring can carry the exchange (16-byte accesses,
+    // 17-quad row pitch: conflict-free).
+    if (warp == 4) CFB_TR(4);
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const uint32_t xrow = ptx::smem_u32(smem + kOffKV) + (quarter * 32 + lane) * kXPitch * 4;
+    const uint32_t xrow = sbase + kOffKV + ii * kXPitch * 4;
     if (set == 1) {
-      ptx::sts_f32(xrow, m_run);
-      ptx::sts_f32(xrow + 4, l_run);
+      ptx::sts128(xrow, __float_as_uint(m_run), __float_as_uint(l_run), 0u, 0u);
 #pragma unroll
       for (int c = 0; c < kDK / 4; ++c)
         ptx::sts128(xrow + 16 + 16 * c, __float_as_uint(o_acc[4 * c]), __float_as_uint(o_acc[4 * c + 1]),
@@ -402,42 +504,50 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (set == 0) {
-      const float m1 = ptx::lds_f32(xrow), l1 = ptx::lds_f32(xrow + 4);
+      const float4 ml = lds_f32x4(xrow);
+      const float m1 = ml.x, l1 = ml.y;
       const float m = fmaxf(m_run, m1);  // set 0 always owns key tile 0, so m is finite
       const float w0 = fast_exp2((m_run - m) * scale), w1 = fast_exp2((m1 - m) * scale);
       const float l = l_run * w0 + l1 * w1;
       const float inv = (i < len && l > 0.f) ? 1.f / l : 0.f;  // padded query rows -> zeros
-      float o1a[32], o1b[32];
-      ptx::lds_f32x32(xrow + 16, o1a);
-      ptx::lds_f32x32(xrow + 16 + 128, o1b);
+      const float c0 = w0 * inv, c1 = w1 * inv;
       if (i < T) {
         uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(b) * T + i) * p.Dp + h * kDK);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float r[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            r[e] = (o_acc[8 * c + e] * w0 + (c < 4 ? o1a[8 * c + e] : o1b[8 * (c - 4) + e]) * w1) * inv;
+          const float4 x0 = lds_f32x4(xrow + 16 + 32 * c), x1 = lds_f32x4(xrow + 32 + 32 * c);
           uint4 u;
-          u.x = ptx::pack_bf16x2(r[0], r[1]);
-          u.y = ptx::pack_bf16x2(r[2], r[3]);
-          u.z = ptx::pack_bf16x2(r[4], r[5]);
-          u.w = ptx::pack_bf16x2(r[6], r[7]);
+          u.x = ptx::pack_bf16x2(fmaf(o_acc[8 * c + 0], c0, x0.x * c1), fmaf(o_acc[8 * c + 1], c0, x0.y * c1));
+          u.y = ptx::pack_bf16x2(fmaf(o_acc[8 * c + 2], c0, x0.z * c1), fmaf(o_acc[8 * c + 3], c0, x0.w * c1));
+          u.z = ptx::pack_bf16x2(fmaf(o_acc[8 * c + 4], c0, x1.x * c1), fmaf(o_acc[8 * c + 5], c0, x1.y * c1));
+          u.w = ptx::pack_bf16x2(fmaf(o_acc[8 * c + 6], c0, x1.z * c1), fmaf(o_acc[8 * c + 7], c0, x1.w * c1));
           o[c] = u;
         }
       }
     }
   }
 
+  if (warp == 4) CFB_TR(5);
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (warp == 4) CFB_TR(6);
+#undef CFB_TR
 }
 
+long long* g_attn_trace = nullptr;
+
 }  // namespace
+
+// debug: copies the clock trace of the last traced launch to the host (1024 values)
+extern "C" __attribute__((visibility("default"))) int cfb_debug_attn_trace(long long* host_out) {
+  if (!g_attn_trace) return 1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(host_out, g_attn_trace, 1024 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+}
 
 int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
   if (a.B <= 0 || a.T <= 0) return 0;
@@ -465,7 +575,9 @@ int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!configured[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(rel_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    cudaError_t e = cudaFuncSetAttribute(rel_attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(rel_attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
     if (e != cudaSuccess) {
       if (err) *err = std::string("cudaFuncSetAttribute(attn_tc): ") + cudaGetErrorString(e);
       return static_cast<int>(e);
@@ -479,8 +591,23 @@ int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
   p.T = a.T;
   p.Dp = Dp;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(a.dk));
+  p.trace = nullptr;
+  {
+    const char* dbg = getenv("CFB_ATTN_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  if (getenv("CFB_ATTN_TRACE")) {
+    if (!g_attn_trace) {
+      cudaMalloc(&g_attn_trace, 1024 * sizeof(long long));
+      cudaMemset(g_attn_trace, 0, 1024 * sizeof(long long));
+    }
+    p.trace = g_attn_trace;
+  }
   dim3 grid((a.T + kBM - 1) / kBM, a.H, a.B);
-  rel_attn_tc_kernel<<<grid, kThreads, kSmemTotal, st>>>(tmKV, tmP, p);
+  if (p.trace != nullptr || p.debug != 0)
+    rel_attn_tc_kernel<true><<<grid, kThreads, kSmemTotal, st>>>(tmKV, tmP, p);
+  else
+    rel_attn_tc_kernel<false><<<grid, kThreads, kSmemTotal, st>>>(tmKV, tmP, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (err) *err = std::string("attn_tc launch: ") + cudaGetErrorString(e);
