@@ -53,6 +53,32 @@ struct ConvDesc {
   int To = 0, Fo = 0;  // output extents
 };
 
+// row-complete GEMM with fused residual update and LayerNorm(s) (gemm_ln.cu):
+//   v = resid + alpha * (A W^T + bias);  y = LN1(v) if gamma1 else v;  out_f32 = y;  out_bf16 = LN2(y) if gamma2 else y
+// lens != null: rows at frames >= lens[row / frames_per_seq] are written as zeros in both outputs
+struct GemmLnDesc {
+  const void* A = nullptr;
+  long long lda = 0;
+  const void* W = nullptr;
+  long long ldw = 0;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;
+  float alpha = 1.f;
+  const float* resid = nullptr;
+  long long ld_resid = 0;
+  const float* gamma1 = nullptr;
+  const float* beta1 = nullptr;
+  const float* gamma2 = nullptr;
+  const float* beta2 = nullptr;
+  float* out_f32 = nullptr;
+  long long ld_out_f32 = 0;
+  void* out_bf16 = nullptr;
+  long long ld_out_bf16 = 0;
+  const int32_t* lens = nullptr;
+  int frames_per_seq = 1;
+};
+int launch_gemm_ln(const GemmLnDesc& g, cudaStream_t st, std::string* err);
+
 struct AttnDesc {
   const void* qkv = nullptr;  // (B*T, 4*Dp)
   const void* pos = nullptr;  // (2T-1, ld_pos), this layer's columns start at pos
@@ -71,6 +97,9 @@ int launch_attn_simt(const AttnDesc& a, cudaStream_t st, std::string* err);
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int rows, int d,
                      const int32_t* lens, int frames_per_seq, cudaStream_t st);
+// y = LN(x; g1, b1) -> out1 (fp32, may alias x); LN(y; g2, b2) -> out2 (bf16): norm_out + the next layer's first norm
+int launch_layernorm_dual(const float* x, const float* g1, const float* b1, float* out1, const float* g2, const float* b2,
+                          void* out2_bf16, int rows, int d, cudaStream_t st);
 int launch_depthwise(const void* x, const float* taps, const float* bias, void* out, bool is_bf16, int B, int T, int d,
                      int ksize, cudaStream_t st);
 int launch_lengths(const long long* lengths, int32_t* out, int B, int T_full, int n_stages, cudaStream_t st);

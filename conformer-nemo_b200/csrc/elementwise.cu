@@ -83,6 +83,78 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// norm_out of one layer followed by norm_feed_forward1 of the next (conformer_modules.py:120 then :98 of the next
+// layer) in one pass: y = LN1(x) is written back as the fp32 residual stream and LN2(y) as the bf16 GEMM operand.
+// Saves one full read of the stream and one launch per layer.  Same one-warp-per-row scheme as layernorm_kernel.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_dual_kernel(const float* __restrict__ x, const float* __restrict__ g1,
+                                                             const float* __restrict__ b1, float* __restrict__ out1,
+                                                             const float* __restrict__ g2, const float* __restrict__ b2,
+                                                             bf16* __restrict__ out2, int rows, int d) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  constexpr int kN = NV > 0 ? NV : kMaxVec;
+  const int nvec = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * d);
+  float4 v[kN];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kN; ++k) {
+    const int i = lane + 32 * k;
+    if (NV > 0 || i < nvec) {
+      v[k] = __ldcs(xr + i);
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  const float inv_d = 1.0f / static_cast<float>(d);
+  float mean = warp_sum(s) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < kN; ++k) {
+    const int i = lane + 32 * k;
+    if (NV > 0 || i < nvec) {
+      v[k].x -= mean, v[k].y -= mean, v[k].z -= mean, v[k].w -= mean;
+      q += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
+    }
+  }
+  float rstd = 1.0f / sqrtf(warp_sum(q) * inv_d + 1e-5f);
+  s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kN; ++k) {
+    const int i = lane + 32 * k;
+    if (NV > 0 || i < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(g1) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(b1) + i);
+      v[k].x = fmaf(v[k].x * rstd, g.x, b.x), v[k].y = fmaf(v[k].y * rstd, g.y, b.y);
+      v[k].z = fmaf(v[k].z * rstd, g.z, b.z), v[k].w = fmaf(v[k].w * rstd, g.w, b.w);
+      store4(out1 + static_cast<long long>(row) * d + 4 * i, v[k].x, v[k].y, v[k].z, v[k].w);
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+  }
+  mean = warp_sum(s) * inv_d;
+  q = 0.f;
+#pragma unroll
+  for (int k = 0; k < kN; ++k) {
+    const int i = lane + 32 * k;
+    if (NV > 0 || i < nvec) {
+      v[k].x -= mean, v[k].y -= mean, v[k].z -= mean, v[k].w -= mean;
+      q += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
+    }
+  }
+  rstd = 1.0f / sqrtf(warp_sum(q) * inv_d + 1e-5f);
+#pragma unroll
+  for (int k = 0; k < kN; ++k) {
+    const int i = lane + 32 * k;
+    if (NV > 0 || i < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(g2) + i);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(b2) + i);
+      store4(out2 + static_cast<long long>(row) * d + 4 * i, fmaf(v[k].x * rstd, g.x, b.x), fmaf(v[k].y * rstd, g.y, b.y),
+             fmaf(v[k].z * rstd, g.z, b.z), fmaf(v[k].w * rstd, g.w, b.w));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ depth-wise conv
 // out[b,t,c] = swish(bias[c] + sum_k taps[k][c] * x[b, t + k - (K-1)/2, c]), zero outside [0,T); taps are (K, d).
 // Block: 64 channels x 128 frames of one sequence.  The (128 + K - 1)-frame halo tile is staged in shared memory in
@@ -350,6 +422,18 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
     else CFB_LN(float, 0);
   }
 #undef CFB_LN
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_layernorm_dual(const float* x, const float* g1, const float* b1, float* out1, const float* g2, const float* b2,
+                          void* out2_bf16, int rows, int d, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (d % 4 != 0 || d > 128 * kMaxVec) return -1;
+  const int blocks = (rows + 7) / 8;
+  bf16* o2 = reinterpret_cast<bf16*>(out2_bf16);
+  if (d == 512) layernorm_dual_kernel<4><<<blocks, 256, 0, st>>>(x, g1, b1, out1, g2, b2, o2, rows, d);
+  else if (d == 256) layernorm_dual_kernel<2><<<blocks, 256, 0, st>>>(x, g1, b1, out1, g2, b2, o2, rows, d);
+  else layernorm_dual_kernel<0><<<blocks, 256, 0, st>>>(x, g1, b1, out1, g2, b2, o2, rows, d);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -1,6 +1,9 @@
 // cuTensorMapEncodeTiled without linking libcuda: the entry point is resolved through the CUDA runtime, so the
 // shared library loads (and exports its symbols) on a machine that has no driver installed.
+#include <string.h>
+
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -28,6 +31,40 @@ bool encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64
 
 bool encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
                  const uint64_t* strides_bytes, const uint32_t* box, std::string* err) {
+  // A forward pass re-encodes the same few hundred descriptors on every call (same workspace, same shapes); the
+  // driver call costs ~1-2 us each, which is visible at 260 launches per forward.  Per-thread cache, no locking.
+  struct Key {
+    const void* base;
+    uint64_t dims[5], strides[4];
+    uint32_t box[5];
+    int rank, f32;
+    bool operator==(const Key& o) const { return memcmp(this, &o, sizeof(Key)) == 0; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+      uint64_t hsh = 1469598103934665603ull;
+      for (size_t i = 0; i < sizeof(Key) / 8; ++i) hsh = (hsh ^ w[i]) * 1099511628211ull;
+      return static_cast<size_t>(hsh);
+    }
+  };
+  static_assert(sizeof(Key) % 8 == 0, "Key is hashed as 64-bit words");
+  thread_local std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  Key key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.rank = rank;
+  key.f32 = is_f32 ? 1 : 0;
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i + 1 < rank) key.strides[i] = strides_bytes[i];
+  }
+  auto hit = cache.find(key);
+  if (hit != cache.end()) {
+    *map = hit->second;
+    return true;
+  }
   std::call_once(g_once, resolve);
   if (g_encode == nullptr) {
     if (err) *err = "cuTensorMapEncodeTiled is not available (no CUDA driver?)";
@@ -57,6 +94,8 @@ bool encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, cons
     }
     return false;
   }
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *map);
   return true;
 }
 

@@ -172,6 +172,9 @@ class ConformerEncoder(nn.Module):
         self._handle_device = None
         self._dirty = True         # parameters changed since the last prepare()
         self._workspace = None
+        self._use_graphs = False   # enable_cuda_graphs(): replay one captured graph per input shape
+        self._graphs = OrderedDict()
+        self._profiling = False
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.mark_weights_dirty())
         self.eval()
 
@@ -214,14 +217,27 @@ class ConformerEncoder(nn.Module):
         prev, self.use_pad_mask = self.use_pad_mask, on
         return prev
 
+    # ------------------------------------------------------------------------------------------------ CUDA graphs
+    def enable_cuda_graphs(self, on: bool = True, max_shapes: int = 4) -> None:
+        """cfb_forward only enqueues kernels (no allocation, no synchronisation), so a forward can be captured once
+        per input shape and replayed: the ~260 launches of a step then cost one driver call.  With graphs on,
+        ``forward`` copies its inputs into the graph's static buffers, replays, and returns views of the graph's
+        static output buffers -- they are overwritten by the next forward of the same shape."""
+        self._use_graphs = bool(on)
+        self._graph_cap = max(1, int(max_shapes))
+        if not on:
+            self._graphs.clear()
+
     # ------------------------------------------------------------------------------------------------ weights
     def mark_weights_dirty(self) -> None:
         """Parameters are copied into the library's own arena; call this after modifying them in place
         (``load_state_dict`` and ``.to()`` / ``.cuda()`` do it automatically)."""
         self._dirty = True
+        self._graphs.clear()  # captured graphs read the old weight arena
 
     def _apply(self, fn, *args, **kwargs):  # .to()/.cuda()/.half(): weights must be re-packed
         self._dirty = True
+        self.__dict__.get("_graphs", {}).clear()
         return super()._apply(fn, *args, **kwargs)
 
     def prepare(self, device: Optional[torch.device] = None) -> None:
@@ -317,6 +333,8 @@ class ConformerEncoder(nn.Module):
                 raise TypeError(f"length must have shape ({b},), got {tuple(length.shape)}")
             length = length.to(device=device, dtype=torch.int64).contiguous()
         t_out = self.output_frames(t)
+        if self._use_graphs and not self._profiling and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graph(feats, length, out_dtype, b, t, t_out, device)
         encoded = torch.empty(b, t_out, self._feat_out, dtype=out_dtype, device=device)
         encoded_len = torch.empty(b, dtype=torch.int32, device=device)
         nbytes = ctypes.c_size_t()
@@ -332,12 +350,47 @@ class ConformerEncoder(nn.Module):
                 ctypes.c_void_p(ws_ptr), nbytes.value, ctypes.c_void_p(stream)), self._handle, "cfb_forward")
         return encoded.transpose(1, 2), encoded_len
 
+    def _forward_graph(self, feats, length, out_dtype, b, t, t_out, device):
+        key = (b, t, feats.dtype, length is not None, out_dtype, device.index)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_feats = torch.empty_like(feats)
+            static_len = torch.empty(b, dtype=torch.int64, device=device) if length is not None else None
+            static_feats.copy_(feats)
+            if length is not None:
+                static_len.copy_(length)
+            self._use_graphs = False
+            try:
+                side = torch.cuda.Stream(device=device)
+                side.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(side):  # warm-up outside capture (workspace allocation, lazy module loading)
+                    self.forward_for_export(static_feats, static_len, out_dtype)
+                torch.cuda.current_stream(device).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    enc_t, enc_len = self.forward_for_export(static_feats, static_len, out_dtype)
+            finally:
+                self._use_graphs = True
+            # the entry keeps the workspace the graph was captured with alive
+            entry = (graph, static_feats, static_len, enc_t, enc_len, self._workspace)
+            self._graphs[key] = entry
+            while len(self._graphs) > getattr(self, "_graph_cap", 4):
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
+            entry[1].copy_(feats)
+            if length is not None:
+                entry[2].copy_(length)
+        entry[0].replay()
+        return entry[3], entry[4]
+
     # profiling ---------------------------------------------------------------------------------------------------
     def set_profiling(self, on: bool) -> None:
         """Bracket every kernel of subsequent forwards with CUDA events (cfb_set_profiling)."""
         if self._handle is None:
             self.prepare()
         _lib.check(_lib.load_library().cfb_set_profiling(self._handle, int(on)), self._handle, "cfb_set_profiling")
+        self._profiling = bool(on)
 
     def profile_report(self):
         """{label: (launches, total_ms)} for the forwards since the last report (synchronises)."""

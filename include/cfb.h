@@ -144,6 +144,17 @@ CFB_API int cfb_op_gemm(int use_tensor_cores, int epilogue, const void* A, int64
                 float alpha, const int32_t* lens, int frames_per_seq, int qkv_dp, float* scratch,
                 cfb_stream stream);
 
+/* Row-complete GEMM with the residual update and the following LayerNorm(s) fused (tcgen05 path only, N <= 512):
+ *   v = resid + alpha * (A W^T + bias)         (resid may be NULL)          conformer_modules.py:98-118
+ *   y = LayerNorm(v; gamma1, beta1) if gamma1 else v                        (norm_out, :120)
+ *   out_f32  (M x N fp32, may alias resid) = y
+ *   out_bf16 (M x N bf16) = LayerNorm(y; gamma2, beta2) if gamma2 else y    (the next block's input normalisation)
+ * lens != NULL: rows at frames >= lens[row / frames_per_seq] are written as zeros in both outputs. */
+CFB_API int cfb_op_gemm_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float alpha,
+                   const float* resid, int64_t ld_resid, const float* gamma1, const float* beta1, const float* gamma2,
+                   const float* beta2, int M, int N, int K, float* out_f32, int64_t ld_out_f32, void* out_bf16,
+                   int64_t ld_out_bf16, const int32_t* lens, int frames_per_seq, cfb_stream stream);
+
 /* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5; conformer_modules.py:60-86). x fp32 (rows x d);
  * out_dtype CFB_BF16 / CFB_F32.  lens != NULL: rows at frames >= lens[seq] are written as zeros. */
 CFB_API int cfb_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows,

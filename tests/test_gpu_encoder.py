@@ -177,3 +177,30 @@ def test_cuda_graph_capture_of_forward():
     assert torch.equal(len_cap, len_new)
     assert float((y_cap - y_new).abs().max()) == 0.0
     assert float((y_cap - y_ref).abs().max()) > 0.0
+
+
+def test_enable_cuda_graphs_matches_eager_and_tracks_shapes():
+    """ConformerEncoder.enable_cuda_graphs(): one captured graph per input shape, replayed on later calls; results
+    are bit-identical to the eager launches, including length=None and a second shape."""
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=2, d_model=256, n_heads=4)
+    sd = oc.random_state_dict(cfg, 52)
+    enc = build(cfg, sd, "bf16")
+    cases = []
+    for seed, (b, t, lens) in enumerate([(2, 320, [320, 200]), (2, 320, [100, 320]), (3, 200, [200, 150, 9])]):
+        x, length = oc.synthetic_batch(b, 80, t, lens, seed=20 + seed)
+        cases.append((x.cuda(), length.cuda()))
+    eager = [tuple(v.clone() for v in enc(audio_signal=x, length=l)) for x, l in cases]
+    eager_none = enc(audio_signal=cases[0][0], length=None)[0].clone()
+    enc.enable_cuda_graphs(True)
+    for rep in range(2):  # first pass captures, second pass replays
+        for (x, l), (y0, l0) in zip(cases, eager):
+            y, ylen = enc(audio_signal=x, length=l)
+            torch.cuda.synchronize()
+            assert torch.equal(ylen, l0)
+            assert float((y - y0).abs().max()) == 0.0
+        y, _ = enc(audio_signal=cases[0][0], length=None)
+        assert float((y - eager_none).abs().max()) == 0.0
+    assert len(enc._graphs) == 3
+    enc.enable_cuda_graphs(False)
+    y, _ = enc(audio_signal=cases[0][0], length=cases[0][1])
+    assert float((y - eager[0][0]).abs().max()) == 0.0
