@@ -101,7 +101,6 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int T = p.T;
-  const int len = min(p.lens[b], T);
   uint32_t tid;
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));  // volatile: keeps warp / lane in registers (no S2R re-reads)
   const int warp = tid >> 5;
@@ -110,19 +109,6 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   const int dbg = kInstr ? p.debug : 0;
 #define CFB_TR(slot) do { if (kInstr && trc) p.trace[slot] = clock64(); } while (0)
   if (warp == 4) CFB_TR(0);
-
-  if (i0 >= len) {
-    // the whole query tile is padding: context is zero (block-uniform exit, nothing allocated yet)
-    if (warp >= 4 && warp < 8) {
-      const int i = i0 + (warp & 3) * 32 + lane;
-      if (i < T) {
-        uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(b) * T + i) * p.Dp + h * kDK);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) o[c] = make_uint4(0, 0, 0, 0);
-      }
-    }
-    return;
-  }
 
   extern __shared__ uint8_t smem_raw[];
   // every shared-memory object is addressed through a 32-bit shared address derived once from this base
@@ -144,26 +130,8 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   const uint32_t tmem_slot = g_full + 8 * kGSlots;
   static_assert(112 + 8 * (2 * kKVStages + 2 * kBandSlots + kGSlots) + 8 <= 256, "barrier area");
 
-  const int n_kt = (len + kBN - 1) / kBN;
-  const int n_gb = n_kt + 2;  // G blocks 0 .. n_kt+1
-
-  uint32_t qw[32];  // softmax warps: this thread's row of Q+u (set 0) / Q+v (set 1), 64 bf16, fetched before the setup
-  if (warp >= 4) {
-    const int i = i0 + (warp & 3) * 32 + lane;
-    if (i < T) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<long long>(b) * T + i) * (4 * p.Dp) +
-                                                        ((warp - 4) >> 2) * p.Dp + h * kDK);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 u = __ldg(src + c);
-        qw[4 * c] = u.x, qw[4 * c + 1] = u.y, qw[4 * c + 2] = u.z, qw[4 * c + 3] = u.w;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) qw[c] = 0u;
-    }
-  }
-
+  // Barrier init and the TMEM allocation overlap the previous kernel's tail (programmatic dependent launch);
+  // everything that reads global memory comes after pdl_wait().
   if (warp == 0) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmKV);
@@ -188,22 +156,48 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         ptx::mbar_init_a(exp_done + 8 * s, 4);
       }
       ptx::fence_mbar_init();
-      // the first loads only need their own barriers: issue them before the CTA-wide setup barrier
-      const int r0 = T - 1 - i0 - (kBM - 1);  // band row of G column 0 of block 0 (may be < 0: TMA zero-fills)
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        ptx::mbar_arrive_expect_tx_a(band_full + 8 * g, kBlockBytes);
-        ptx::tma_load_2d_a(sbase + kOffBand + g * kBlockBytes, &tmP, band_full + 8 * g, h * kDK, r0 + 64 * g);
-      }
-      ptx::mbar_arrive_expect_tx_a(kv_full, kKVBytes);
-      ptx::tma_load_2d_a(sbase + kOffKV, &tmKV, kv_full, 2 * p.Dp + h * kDK, b * T);
-      ptx::tma_load_2d_a(sbase + kOffKV + kKBytes, &tmKV, kv_full, 3 * p.Dp + h * kDK, b * T);
     }
     __syncwarp();
   } else if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  const int len = min(p.lens[b], T);
+  const bool active = i0 < len;  // otherwise the whole query tile is padding: the context rows are zero
+  const int n_kt = active ? (len + kBN - 1) / kBN : 0;
+  const int n_gb = n_kt + 2;  // G blocks 0 .. n_kt+1
+
+  uint32_t qw[32];  // softmax warps: this thread's row of Q+u (set 0) / Q+v (set 1), 64 bf16, fetched before the setup
+  if (warp >= 4 && active) {
+    const int i = i0 + (warp & 3) * 32 + lane;
+    if (i < T) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<long long>(b) * T + i) * (4 * p.Dp) +
+                                                        ((warp - 4) >> 2) * p.Dp + h * kDK);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = __ldg(src + c);
+        qw[4 * c] = u.x, qw[4 * c + 1] = u.y, qw[4 * c + 2] = u.z, qw[4 * c + 3] = u.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) qw[c] = 0u;
+    }
+  }
+
+  if (warp == 0 && lane == 0 && active) {
+    // the first loads only need their own barriers: issue them before the CTA-wide setup barrier
+    const int r0 = T - 1 - i0 - (kBM - 1);  // band row of G column 0 of block 0 (may be < 0: TMA zero-fills)
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      ptx::mbar_arrive_expect_tx_a(band_full + 8 * g, kBlockBytes);
+      ptx::tma_load_2d_a(sbase + kOffBand + g * kBlockBytes, &tmP, band_full + 8 * g, h * kDK, r0 + 64 * g);
+    }
+    ptx::mbar_arrive_expect_tx_a(kv_full, kKVBytes);
+    ptx::tma_load_2d_a(sbase + kOffKV, &tmKV, kv_full, 2 * p.Dp + h * kDK, b * T);
+    ptx::tma_load_2d_a(sbase + kOffKV + kKBytes, &tmKV, kv_full, 3 * p.Dp + h * kDK, b * T);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -212,7 +206,16 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
   if (warp == 4) CFB_TR(1);
 
-  if (warp < 4) {
+  if (!active) {
+    if (warp >= 4 && warp < 8) {
+      const int i = i0 + (warp & 3) * 32 + lane;
+      if (i < T) {
+        uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(b) * T + i) * p.Dp + h * kDK);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  } else if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
     if (warp == 0) {
       // ---------------------------------------------------------------------------------- TMA producer
@@ -604,11 +607,11 @@ int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
     p.trace = g_attn_trace;
   }
   dim3 grid((a.T + kBM - 1) / kBM, a.H, a.B);
+  cudaError_t e;
   if (p.trace != nullptr || p.debug != 0)
-    rel_attn_tc_kernel<true><<<grid, kThreads, kSmemTotal, st>>>(tmKV, tmP, p);
+    e = launch_pdl(rel_attn_tc_kernel<true>, grid, dim3(kThreads), kSmemTotal, st, tmKV, tmP, p);
   else
-    rel_attn_tc_kernel<false><<<grid, kThreads, kSmemTotal, st>>>(tmKV, tmP, p);
-  cudaError_t e = cudaGetLastError();
+    e = launch_pdl(rel_attn_tc_kernel<false>, grid, dim3(kThreads), kSmemTotal, st, tmKV, tmP, p);
   if (e != cudaSuccess) {
     if (err) *err = std::string("attn_tc launch: ") + cudaGetErrorString(e);
     return static_cast<int>(e);

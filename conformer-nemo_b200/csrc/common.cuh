@@ -88,6 +88,34 @@ struct AttnDesc {
   int B = 0, T = 0, H = 0, dk = 0, dkp = 0;
 };
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// Every product-path kernel is launched with programmaticStreamSerialization: its CTAs may start (barrier init,
+// TMEM allocation, descriptor prefetch) while the previous kernel of the stream drains, and they call pdl_wait()
+// before their first global-memory access -- it returns once the previous kernel has completed and flushed.
+// pdl_launch_dependents() at the top of a kernel lets the NEXT kernel start the same way.  The forward is a chain
+// of ~260 short dependent launches, so this can hide launch latency + prologue per link.  Opt-in (CFB_PDL=1): see
+// pdl_enabled() for the measurement.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- launchers (each returns a cudaError_t-compatible int; 0 = success) ------------------------------------------
 int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err);
 int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err);

@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         int frames_per_seq) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= rows) return;
   constexpr int kN = NV > 0 ? NV : kMaxVec;
   const int nvec = d >> 2;  // float4 per row
@@ -108,6 +110,8 @@ __global__ void __launch_bounds__(256) layernorm_dual_kernel(const float* __rest
                                                              bf16* __restrict__ out2, int rows, int d) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= rows) return;
   constexpr int kN = NV > 0 ? NV : kMaxVec;
   const int nvec = d >> 2;
@@ -222,6 +226,8 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const T* __restrict__ x,
   T* ob = out + static_cast<long long>(b) * T_len * d;
   const int span = kDwT + ksize - 1;
   static_assert((kChunks & (kChunks - 1)) == 0, "chunks per row must be a power of two");
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < span * kChunks; i += 256) {
     const int r = i / kChunks, ch = i & (kChunks - 1);
     const int t = t0 - half + r, c = c0 + ch * kVec;
@@ -295,6 +301,8 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const T* __restrict__ x,
 __global__ void lengths_kernel(const long long* __restrict__ lengths, int32_t* __restrict__ out, int B, int T_full,
                                int n_stages) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (i >= B) return;
   if (lengths == nullptr) {
     float f = static_cast<float>(T_full);  // length=None: every row is T_full long (conformer_encoder.py:243-246)
@@ -313,6 +321,8 @@ __global__ void lengths_kernel(const long long* __restrict__ lengths, int32_t* _
 template <typename TOut>
 __global__ void pos_table_kernel(TOut* __restrict__ out, const float* __restrict__ div_term, int T, int d) {
   const int k = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const float pos = static_cast<float>(T - 1 - k);
   for (int m = threadIdx.x; m < d / 2; m += blockDim.x) {
     const float ang = __fmul_rn(pos, div_term[m]);
@@ -340,6 +350,8 @@ __global__ void __launch_bounds__(256) subsample_first_kernel(const TIn* __restr
   const int b = blockIdx.x / tblocks;
   const int t1_0 = (blockIdx.x % tblocks) * kS1T;
   const TIn* xb = feats + static_cast<long long>(b) * F * T;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < (F + 2) * (2 * kS1T + 1); i += 256) {
     const int fr = i / (2 * kS1T + 1), tc = i % (2 * kS1T + 1);
     const int f = fr - 1, t = 2 * t1_0 - 1 + tc;
@@ -427,8 +439,8 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
   if (d % 4 != 0 || d > 128 * kMaxVec) return -1;
   const int blocks = (rows + 7) / 8;
 #define CFB_LN(T, NV)                                                                                          \
-  layernorm_kernel<T, NV><<<blocks, 256, 0, st>>>(x, gamma, beta, reinterpret_cast<T*>(out), rows, d, lens,   \
-                                                  frames_per_seq)
+  launch_pdl(layernorm_kernel<T, NV>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, reinterpret_cast<T*>(out), rows, \
+             d, lens, frames_per_seq)
   if (out_bf16) {
     if (d == 512) CFB_LN(bf16, 4);
     else if (d == 256) CFB_LN(bf16, 2);
@@ -448,9 +460,9 @@ int launch_layernorm_dual(const float* x, const float* g1, const float* b1, floa
   if (d % 4 != 0 || d > 128 * kMaxVec) return -1;
   const int blocks = (rows + 7) / 8;
   bf16* o2 = reinterpret_cast<bf16*>(out2_bf16);
-  if (d == 512) layernorm_dual_kernel<4><<<blocks, 256, 0, st>>>(x, g1, b1, out1, g2, b2, o2, rows, d);
-  else if (d == 256) layernorm_dual_kernel<2><<<blocks, 256, 0, st>>>(x, g1, b1, out1, g2, b2, o2, rows, d);
-  else layernorm_dual_kernel<0><<<blocks, 256, 0, st>>>(x, g1, b1, out1, g2, b2, o2, rows, d);
+  if (d == 512) launch_pdl(layernorm_dual_kernel<4>, dim3(blocks), dim3(256), 0, st, x, g1, b1, out1, g2, b2, o2, rows, d);
+  else if (d == 256) launch_pdl(layernorm_dual_kernel<2>, dim3(blocks), dim3(256), 0, st, x, g1, b1, out1, g2, b2, o2, rows, d);
+  else launch_pdl(layernorm_dual_kernel<0>, dim3(blocks), dim3(256), 0, st, x, g1, b1, out1, g2, b2, o2, rows, d);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -461,11 +473,11 @@ int launch_depthwise(const void* x, const float* taps, const float* bias, void* 
   dim3 grid(B * ((T + kDwT - 1) / kDwT), (d + kDwC - 1) / kDwC);
   if (is_bf16) {
     if (ksize == 31)
-      depthwise_kernel<bf16, true, 31><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), taps, bias,
-                                                             reinterpret_cast<bf16*>(out), T, d, ksize);
+      launch_pdl(depthwise_kernel<bf16, true, 31>, grid, dim3(256), 0, st, reinterpret_cast<const bf16*>(x), taps, bias,
+                 reinterpret_cast<bf16*>(out), T, d, ksize);
     else
-      depthwise_kernel<bf16, true, 0><<<grid, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), taps, bias,
-                                                            reinterpret_cast<bf16*>(out), T, d, ksize);
+      launch_pdl(depthwise_kernel<bf16, true, 0>, grid, dim3(256), 0, st, reinterpret_cast<const bf16*>(x), taps, bias,
+                 reinterpret_cast<bf16*>(out), T, d, ksize);
   } else {
     depthwise_kernel<float, false, 0><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), taps, bias,
                                                             reinterpret_cast<float*>(out), T, d, ksize);
@@ -475,14 +487,14 @@ int launch_depthwise(const void* x, const float* taps, const float* bias, void* 
 
 int launch_lengths(const long long* lengths, int32_t* out, int B, int T_full, int n_stages, cudaStream_t st) {
   if (B <= 0) return 0;
-  lengths_kernel<<<(B + 127) / 128, 128, 0, st>>>(lengths, out, B, T_full, n_stages);
+  launch_pdl(lengths_kernel, dim3((B + 127) / 128), dim3(128), 0, st, lengths, out, B, T_full, n_stages);
   return static_cast<int>(cudaGetLastError());
 }
 
 int launch_pos_table(void* out, bool out_bf16, const float* div_term, int T, int d, cudaStream_t st) {
   if (T <= 0) return 0;
   if (out_bf16)
-    pos_table_kernel<bf16><<<2 * T - 1, 128, 0, st>>>(reinterpret_cast<bf16*>(out), div_term, T, d);
+    launch_pdl(pos_table_kernel<bf16>, dim3(2 * T - 1), dim3(128), 0, st, reinterpret_cast<bf16*>(out), div_term, T, d);
   else
     pos_table_kernel<float><<<2 * T - 1, 128, 0, st>>>(reinterpret_cast<float*>(out), div_term, T, d);
   return static_cast<int>(cudaGetLastError());
@@ -498,9 +510,8 @@ int launch_subsample_first(const void* feats, bool feats_bf16, const float* w9, 
   const int gpb = groups < 64 ? groups : 64;  // channel groups per block; the other threads walk positions
   const dim3 grid(B * tblocks, (groups + gpb - 1) / gpb);
 #define CFB_S1(TIN, TOUT)                                                                                         \
-  subsample_first_kernel<TIN, TOUT><<<grid, 256, smem, st>>>(reinterpret_cast<const TIN*>(feats), w9, bias,       \
-                                                             reinterpret_cast<TOUT*>(y_out), F, T, C, T1, F1, Th, \
-                                                             Fh, gpb)
+  launch_pdl(subsample_first_kernel<TIN, TOUT>, grid, dim3(256), smem, st, reinterpret_cast<const TIN*>(feats), w9,  \
+             bias, reinterpret_cast<TOUT*>(y_out), F, T, C, T1, F1, Th, Fh, gpb)
   if (feats_bf16) {
     if (out_bf16)
       CFB_S1(bf16, bf16);

@@ -11,6 +11,7 @@
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop
 // of tile i+1.  M/N/K tails are handled by TMA zero fill on the load side and TMA clipping on the store side.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -35,6 +36,7 @@ struct TcParams {
   int conv_tblocks;   // output tiles per sequence along time (32 frames each)
   int conv_fblocks;   // output tiles along frequency (4 bins each)
   int conv_To, conv_Fo;
+  int dbg_nofence;  // CFB_GEMM_NOFENCE=1: timing experiment only (results may be stale)
   EpiParams ep;
 };
 
@@ -88,6 +90,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();  // the next kernel may begin its own setup
+  pdl_wait();               // the previous kernel's output (A, the residual stream) is complete from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -235,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          ptx::fence_proxy_async_smem();
+          if (!p.dbg_nofence) ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             if constexpr (CONV) {
@@ -300,8 +304,7 @@ int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     configured[dev & 63] = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  kern<<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, tmO, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kThreads), L::kTotal, st, tmA, tmB, tmO, p);
   if (e != cudaSuccess) {
     if (err) *err = std::string("gemm_tc launch: ") + cudaGetErrorString(e);
     return static_cast<int>(e);
@@ -368,6 +371,7 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
   p.num_n_tiles = n_tiles;
   p.num_tiles = m_tiles * n_tiles;
   p.num_k_blocks = (g.K + kBlockK - 1) / kBlockK;
+  p.dbg_nofence = getenv("CFB_GEMM_NOFENCE") != nullptr;
   p.ep = g.ep;
   p.ep.M = g.M;
   p.ep.N = g.N;
