@@ -8,6 +8,8 @@
 //               staged into a 128-byte-swizzled smem box per warp (32 rows x 128 B, double-buffered) and written
 //               with TMA stores -- plain stores for bf16 / fp32 outputs, cp.reduce.async.bulk (.add.f32) into the
 //               fp32 residual stream -- so every global write is a full 128-byte line
+// Operand bytes in flight decide the sustained rate (TMA latency ~1 us vs 270 ns per 48 KB k-block at full tensor
+// rate): 256-wide tiles run 4 stages (192 KB in flight) and pay for the fourth with single-buffered output staging.
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop
 // of tile i+1.  M/N/K tails are handled by TMA zero fill on the load side and TMA clipping on the store side.
 #include <stdio.h>
@@ -40,13 +42,15 @@ struct TcParams {
   EpiParams ep;
 };
 
-template <int BN, int STAGES>
+// SBUF = staging boxes per epilogue warp (2 = double-buffered TMA stores; 1 frees 32 KB for one more operand stage)
+template <int BN, int STAGES, int SBUF = (BN == 256 ? 1 : 2)>
 struct SmemLayout {
+  static constexpr int kSBuf = SBUF;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingOffset = STAGES * kStageBytes;  // per epilogue warp: 2 buffers x (32 rows x 128 B)
-  static constexpr int kStagingBytes = kEpiWarps * 2 * 4096;
+  static constexpr int kStagingBytes = kEpiWarps * SBUF * 4096;
   static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
   static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
@@ -173,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3;        // TMEM lanes this warp may read: [32*quarter, +32)
     const int half = (warp - 2) >> 2;    // which of the quarter's two warps: takes boxes half, half+2, ...
     const int row_in_tile = quarter * 32 + lane;
-    uint8_t* stage_base = smem + L::kStagingOffset + (warp - 2) * 8192;
+    uint8_t* stage_base = smem + L::kStagingOffset + (warp - 2) * (L::kSBuf * 4096);
     const uint32_t swz = static_cast<uint32_t>(lane & 7);
     uint32_t box_counter = 0;
     int it = 0;
@@ -208,8 +212,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_pass = (EPI == EPI_QKV && acc_col0 < p.ep.qkv_dp) ? 2 : 1;
 #pragma unroll 1
         for (int pass = 0; pass < n_pass; ++pass) {
-          uint8_t* sbuf = stage_base + (box_counter & 1u) * 4096;
-          if (lane == 0) ptx::bulk_wait_read<1>();  // the store that last read this buffer has drained it
+          uint8_t* sbuf = stage_base + (L::kSBuf == 2 ? (box_counter & 1u) * 4096 : 0u);
+          if (lane == 0) {  // the store that last read this buffer has drained it
+            if constexpr (L::kSBuf == 2) ptx::bulk_wait_read<1>();
+            else ptx::bulk_wait_read<0>();
+          }
           __syncwarp();
           uint8_t* srow = sbuf + lane * 128;
 #pragma unroll
@@ -391,7 +398,7 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
     uint32_t box[2] = {f32 ? 32u : 64u, 32u};
     if (!encode_tmap(&tmO, g.ep.out, f32, 2, dims, strides, box, err)) return -1;
   }
-  if (bn == 256) return dispatch_epi<256, 3, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
+  if (bn == 256) return dispatch_epi<256, 4, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
   return dispatch_epi<128, 5, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
 }
 
@@ -443,7 +450,7 @@ int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err) {
     uint32_t box[4] = {64, 4, 8, 1};
     if (!encode_tmap_bf16(&tmO, c.y_out, 4, dims, strides, box, err)) return -1;
   }
-  if (bn == 256) return dispatch_epi<256, 3, true>(EPI_RELU, true, tmA, tmB, tmO, p, st, err);
+  if (bn == 256) return dispatch_epi<256, 4, true>(EPI_RELU, true, tmA, tmB, tmO, p, st, err);
   return dispatch_epi<128, 5, true>(EPI_RELU, true, tmA, tmB, tmO, p, st, err);
 }
 
