@@ -291,6 +291,14 @@ def run_b200(args):
             enc(audio_signal=xd, length=ld)
             if i == 0:
                 launches_per_step += enc.last_launch_count()
+    if args.ncu:
+        # profiling helper: 3 warm-up steps above, ONE eager step here, nothing else (no graphs, no e2e, no JSON):
+        #   ncu -s <3 * launches/step> -c <launches/step> ... python bench.py --ncu
+        step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(json.dumps({"ncu_helper": True, "launches_per_step": launches_per_step}))
+        return
     # a fresh box needs a moment of sustained load before clocks / power state settle: keep warming for ~1 s
     torch.cuda.synchronize()
     t_warm = time.time()
@@ -520,6 +528,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="3 warm-up steps + 1 eager step only (for ncu -s/-c)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every step eagerly (no CUDA graph replay)")
     args = ap.parse_args()
     if args.impl == "reference":

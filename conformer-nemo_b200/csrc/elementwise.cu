@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int k = 0; k < kN; ++k) {
     const int i = lane + 32 * k;
     if (NV > 0 || i < nvec) {
-      v[k] = __ldcs(xr + i);
+      v[k] = __ldg(xr + i);
       s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
     }
   }
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) layernorm_dual_kernel(const float* __rest
   for (int k = 0; k < kN; ++k) {
     const int i = lane + 32 * k;
     if (NV > 0 || i < nvec) {
-      v[k] = __ldcs(xr + i);
+      v[k] = __ldg(xr + i);
       s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
     }
   }
