@@ -225,7 +225,8 @@ def build_batches(args, kw, rank, world):
 
         rnd = random.Random(1234)  # len ~ U[200, 3000] frames, seed 1234
         lengths = [rnd.randint(200, 3000) for _ in range(64)]
-        plan = plan_shards(lengths, world, max_batch=32, bucket_frames=256)
+        bucket = args.bucket_frames if args.bucket_frames == "auto" else int(args.bucket_frames)
+        plan = plan_shards(lengths, world, max_batch=args.max_batch, bucket_frames=bucket)
         g = torch.Generator().manual_seed(1234)
         out = []
         for sub in plan.batches[rank]:
@@ -235,7 +236,8 @@ def build_batches(args, kw, rank, world):
                 x[row, :, :n] = torch.randn(kw["feat_in"], n, generator=g)
             out.append((x.pin_memory(), torch.tensor(lens, dtype=torch.int64).pin_memory()))
         return out, sum(lengths) * FRAME_SEC, "strong", {"utterances": 64, "frames": "U[200,3000] seed 1234",
-                                                         "sub_batches_rank0": len(out)}
+                                                         "sub_batches_rank0": len(out), "bucket_frames": args.bucket_frames,
+                                                         "max_batch": args.max_batch}
     _, b, t = WORKLOADS[name]
     g = torch.Generator().manual_seed(1234 + rank)
     x = torch.randn(b, kw["feat_in"], t, generator=g).pin_memory()
@@ -255,7 +257,8 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
 
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # rank 0 prints exactly one JSON line on stdout: NCCL's own output (version banner at WARN/INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     kw = WORKLOADS[args.workload][0]
     enc = build_encoder(kw, device)
@@ -528,6 +531,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bucket-frames", default="auto",
+                    help="cfg3: length-bucket width in input frames, or auto (sharding.plan_cost picks it)")
+    ap.add_argument("--max-batch", type=int, default=64, help="cfg3: utterances per sub-batch at most")
     ap.add_argument("--ncu", action="store_true", help="3 warm-up steps + 1 eager step only (for ncu -s/-c)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every step eagerly (no CUDA graph replay)")
     args = ap.parse_args()

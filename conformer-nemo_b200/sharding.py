@@ -43,16 +43,44 @@ class ShardPlan:
         return [i for sub in self.batches[rank] for i in sub]
 
 
-def plan_shards(lengths: Sequence[int], n_ranks: int, max_batch: int = 64, bucket_frames: int = 128,
+# A forward is ~250 dependent kernel launches whatever the batch holds: measured on B200, a sub-batch costs about 1 ms
+# of fixed time on top of its arithmetic (profiles/r01r_bench_cfg3.json vs cfg2).  Expressed in the cost model's unit
+# (FLOPs at the ~0.7 PFLOP/s the big GEMMs sustain) so that padding and launch overhead can be traded off.
+SUB_BATCH_OVERHEAD_FLOPS = 7.0e11
+
+
+def plan_cost(lengths: Sequence[int], plan: "ShardPlan", cost_fn: Callable[[int], float] = None) -> float:
+    """Modelled time of the slowest rank: every sub-batch pays the fixed overhead plus the PADDED cost of its rows."""
+    cost_fn = cost_fn or utterance_cost
+    worst = 0.0
+    for subs in plan.batches:
+        t = 0.0
+        for sub in subs:
+            t += SUB_BATCH_OVERHEAD_FLOPS + len(sub) * cost_fn(max(int(lengths[i]) for i in sub))
+        worst = max(worst, t)
+    return worst
+
+
+def plan_shards(lengths: Sequence[int], n_ranks: int, max_batch: int = 64, bucket_frames=128,
                 cost_fn: Callable[[int], float] = utterance_cost) -> ShardPlan:
     """Deterministic (every rank computes the same plan from the same lengths; no communication).
 
     1. sort utterances by length (descending), assign each to the currently cheapest rank (LPT greedy);
     2. inside a rank, walk its utterances in descending length and start a new sub-batch whenever the batch is full
-       or the length falls more than ``bucket_frames`` input frames below the sub-batch's longest utterance.
+       or the length falls more than ``bucket_frames`` input frames below the sub-batch's longest utterance
+       (``bucket_frames="auto"``: the width in {128 .. 2048, unbounded} that minimises ``plan_cost``).
     """
     if n_ranks < 1:
         raise ValueError("n_ranks must be >= 1")
+    if bucket_frames == "auto":
+        # padding vs. per-sub-batch overhead: take the bucket width with the cheapest modelled slowest rank
+        best = None
+        for width in (128, 256, 512, 1024, 2048, 1 << 30):
+            cand = plan_shards(lengths, n_ranks, max_batch, width, cost_fn)
+            c = plan_cost(lengths, cand, cost_fn)
+            if best is None or c < best[0]:
+                best = (c, cand)
+        return best[1]
     order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
     loads = [0.0] * n_ranks
     per_rank: List[List[int]] = [[] for _ in range(n_ranks)]

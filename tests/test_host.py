@@ -278,3 +278,21 @@ def test_world_size_2_gloo_shards_cover_the_batch():
     for i, n, checksum in flat:
         assert n == single[i][1]
         assert checksum == pytest.approx(float(single[i][0].double().sum()), abs=1e-3)  # thread-count dependent rounding
+
+
+def test_plan_shards_auto_bucket_width_trades_padding_against_launch_overhead():
+    """bucket_frames="auto": covers every utterance once, is never worse than the fixed widths under the plan's own
+    cost model, and uses fewer sub-batches than narrow buckets on a wide length distribution (cfg3)."""
+    import random
+
+    from conformer_nemo_b200.sharding import plan_cost, plan_shards
+
+    rnd = random.Random(1234)
+    lengths = [rnd.randint(200, 3000) for _ in range(64)]
+    for n in (1, 2, 4, 8):
+        auto = plan_shards(lengths, n, 64, "auto")
+        assert sorted(i for r in range(n) for i in auto.rank_indices(r)) == list(range(64))
+        for width in (128, 256, 1024):
+            fixed = plan_shards(lengths, n, 64, width)
+            assert plan_cost(lengths, auto) <= plan_cost(lengths, fixed) + 1e-6
+        assert sum(len(b) for b in auto.batches) < sum(len(b) for b in plan_shards(lengths, n, 64, 128).batches)
