@@ -40,7 +40,7 @@ constexpr int kThreads = 384;  // warpgroup 0: TMA + MMA issuers; warpgroups 1, 
                                // favours high warp ids: issuers placed ABOVE the softmax warps were measured to
                                // steal issue slots with their mbarrier polling, +15 % kernel time.)
 constexpr int kKBytes = kBN * kDK * 2;     // 8 KB
-constexpr int kKVStages = 3;               // K + V tiles, 16 KB per stage
+constexpr int kKVStages = 4;               // K + V tiles, 16 KB per stage
 constexpr int kKVBytes = 2 * kKBytes;
 constexpr int kBandSlots = 3;              // 64-row band blocks in flight (each is consumed by exactly one MMA)
 constexpr int kBlockBytes = 64 * kDK * 2;
@@ -53,7 +53,8 @@ constexpr int kOffKV = 0;
 constexpr int kOffBand = kOffKV + kKVStages * kKVBytes;
 constexpr int kOffShift = kOffBand + kBandSlots * kBlockBytes;
 constexpr int kOffBar = kOffShift + 8 * kShiftBytes;
-constexpr int kSmemTotal = kOffBar + 256 + 1024;
+constexpr int kBarBytes = 512;
+constexpr int kSmemTotal = kOffBar + kBarBytes + 1024;
 static_assert(4 * 32 * kXPitch * 4 <= kKVStages * kKVBytes, "set exchange must fit in the K/V ring");
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColQ = 0, kColS = 64, kColP = 192, kColG = 256;
@@ -128,7 +129,8 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   const uint32_t band_empty = band_full + 8 * kBandSlots;  // [kBandSlots]
   const uint32_t g_full = band_empty + 8 * kBandSlots;   // [kGSlots] G block in TMEM
   const uint32_t tmem_slot = g_full + 8 * kGSlots;
-  static_assert(112 + 8 * (2 * kKVStages + 2 * kBandSlots + kGSlots) + 8 <= 256, "barrier area");
+  static_assert(112 + 8 * (2 * kKVStages + 2 * kBandSlots + kGSlots) + 8 <= kBarBytes, "barrier area");
+  static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
 
   // Barrier init and the TMEM allocation overlap the previous kernel's tail (programmatic dependent launch);
   // everything that reads global memory comes after pdl_wait().

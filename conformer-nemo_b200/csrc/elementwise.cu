@@ -50,52 +50,73 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, TOut* __restrict__ out,
                                                         int rows, int d, const int32_t* __restrict__ lens,
                                                         int frames_per_seq) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // Grid-stride over rows, one warp per row: the NEXT row's loads are issued before the current row is reduced, so a
+  // warp always has a full row (2 KB at d = 512) in flight and blocks are not re-launched every eight rows.
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
   pdl_wait();
   if (row >= rows) return;
   constexpr int kN = NV > 0 ? NV : kMaxVec;
   const int nvec = d >> 2;  // float4 per row
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * d);
-  TOut* orow = out + static_cast<long long>(row) * d;
-  if (lens != nullptr) {
-    const int seq = row / frames_per_seq;
-    if (row - seq * frames_per_seq >= lens[seq]) {
-      for (int i = lane; i < nvec; i += 32) store4(orow + 4 * i, 0.f, 0.f, 0.f, 0.f);
-      return;
-    }
-  }
-  float4 v[kN];
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < kN; ++k) {
-    const int i = lane + 32 * k;
-    if (NV > 0 || i < nvec) {
-      v[k] = __ldg(xr + i);
-      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-    }
-  }
   const float inv_d = 1.0f / static_cast<float>(d);
-  const float mean = warp_sum(s) * inv_d;
-  float q = 0.f;
+  float4 g[kN], b[kN];
 #pragma unroll
   for (int k = 0; k < kN; ++k) {
     const int i = lane + 32 * k;
     if (NV > 0 || i < nvec) {
-      v[k].x -= mean, v[k].y -= mean, v[k].z -= mean, v[k].w -= mean;
-      q += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
+      g[k] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+      b[k] = __ldg(reinterpret_cast<const float4*>(beta) + i);
     }
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(q) * inv_d + 1e-5f);
+  float4 nx[kN];
+  auto fetch = [&](int r) {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(r) * d);
 #pragma unroll
-  for (int k = 0; k < kN; ++k) {
-    const int i = lane + 32 * k;
-    if (NV > 0 || i < nvec) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i);
-      store4(orow + 4 * i, fmaf(v[k].x * rstd, g.x, b.x), fmaf(v[k].y * rstd, g.y, b.y),
-             fmaf(v[k].z * rstd, g.z, b.z), fmaf(v[k].w * rstd, g.w, b.w));
+    for (int k = 0; k < kN; ++k) {
+      const int i = lane + 32 * k;
+      if (NV > 0 || i < nvec) nx[k] = __ldg(xr + i);
+    }
+  };
+  fetch(row);
+  for (; row < rows; row += warps_total) {
+    float4 v[kN];
+#pragma unroll
+    for (int k = 0; k < kN; ++k) v[k] = nx[k];
+    if (row + warps_total < rows) fetch(row + warps_total);
+    TOut* orow = out + static_cast<long long>(row) * d;
+    if (lens != nullptr) {
+      const int seq = row / frames_per_seq;
+      if (row - seq * frames_per_seq >= lens[seq]) {
+        for (int i = lane; i < nvec; i += 32) store4(orow + 4 * i, 0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kN; ++k) {
+      const int i = lane + 32 * k;
+      if (NV > 0 || i < nvec) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < kN; ++k) {
+      const int i = lane + 32 * k;
+      if (NV > 0 || i < nvec) {
+        v[k].x -= mean, v[k].y -= mean, v[k].z -= mean, v[k].w -= mean;
+        q += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * inv_d + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < kN; ++k) {
+      const int i = lane + 32 * k;
+      if (NV > 0 || i < nvec) {
+        store4(orow + 4 * i, fmaf(v[k].x * rstd, g[k].x, b[k].x), fmaf(v[k].y * rstd, g[k].y, b[k].y),
+               fmaf(v[k].z * rstd, g[k].z, b[k].z), fmaf(v[k].w * rstd, g[k].w, b[k].w));
+      }
     }
   }
 }
@@ -437,8 +458,16 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
                      const int32_t* lens, int frames_per_seq, cudaStream_t st) {
   if (rows <= 0) return 0;
   if (d % 4 != 0 || d > 128 * kMaxVec) return -1;
-  const int blocks = (rows + 7) / 8;
-#define CFB_LN(T, NV)                                                                                          \
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  int blocks = (rows + 7) / 8;
+  if (blocks > 4 * sms) blocks = 4 * sms;  // 32 warps per SM, each looping over rows
+#define CFB_LN(T, NV)                                                                                            \
   launch_pdl(layernorm_kernel<T, NV>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, reinterpret_cast<T*>(out), rows, \
              d, lens, frames_per_seq)
   if (out_bf16) {
