@@ -79,6 +79,25 @@ struct GemmLnDesc {
 };
 int launch_gemm_ln(const GemmLnDesc& g, cudaStream_t st, std::string* err);
 
+// GEMM whose A operand is LayerNorm(x) produced in shared memory by a prologue and kept resident (gemm_lna.cu):
+//   [y = LN1(x) -> x_out (fp32)]  optional;  a = bf16(LN2(y or x));  D = a W^T with the EPI_SWISH / QKV / GLU / LINEAR
+//   epilogue (bf16 output).  K = d <= 512.
+struct GemmLnaDesc {
+  const float* x = nullptr;
+  long long ldx = 0;
+  int M = 0, N = 0, d = 0;
+  const float* gamma1 = nullptr;
+  const float* beta1 = nullptr;
+  float* x_out = nullptr;
+  const float* gamma2 = nullptr;
+  const float* beta2 = nullptr;
+  const void* W = nullptr;
+  long long ldw = 0;
+  int epi = EPI_LINEAR;
+  EpiParams ep;
+};
+int launch_gemm_lna(const GemmLnaDesc& g, cudaStream_t st, std::string* err);
+
 struct AttnDesc {
   const void* qkv = nullptr;  // (B*T, 4*Dp)
   const void* pos = nullptr;  // (2T-1, ld_pos), this layer's columns start at pos
@@ -118,6 +137,7 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 
 // ---- launchers (each returns a cudaError_t-compatible int; 0 = success) ------------------------------------------
 int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err);
+long long* g_gemm_trace_view();
 int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err);
 int launch_gemm_simt(const GemmDesc& g, float* scratch, cudaStream_t st, std::string* err);
 int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err);

@@ -1004,6 +1004,36 @@ int cfb_op_gemm_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const
   return rc == 0 ? CFB_OK : op_fail(rc, err);
 }
 
+int cfb_op_gemm_lna(int epilogue, const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* x_out,
+                    const float* gamma2, const float* beta2, const void* W, int64_t ldw, const float* bias,
+                    const float* bias2, int M, int N, int d, void* out, int64_t ldo, const int32_t* lens,
+                    int frames_per_seq, int qkv_dp, cfb_stream stream) {
+  GemmLnaDesc g;
+  g.x = x;
+  g.ldx = ldx;
+  g.M = M;
+  g.N = N;
+  g.d = d;
+  g.gamma1 = gamma1;
+  g.beta1 = beta1;
+  g.x_out = x_out;
+  g.gamma2 = gamma2;
+  g.beta2 = beta2;
+  g.W = W;
+  g.ldw = ldw;
+  g.epi = epilogue;
+  g.ep.bias = bias;
+  g.ep.bias2 = bias2;
+  g.ep.out = out;
+  g.ep.ldo = ldo;
+  g.ep.lens = lens;
+  g.ep.frames_per_seq = frames_per_seq > 0 ? frames_per_seq : 1;
+  g.ep.qkv_dp = qkv_dp;
+  std::string err;
+  int rc = launch_gemm_lna(g, reinterpret_cast<cudaStream_t>(stream), &err);
+  return rc == 0 ? CFB_OK : op_fail(rc, err);
+}
+
 int cfb_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows, int d,
                      const int32_t* lens, int frames_per_seq, cfb_stream stream) {
   int rc = launch_layernorm(x, gamma, beta, out, out_dtype == CFB_BF16, rows, d, lens, frames_per_seq > 0 ? frames_per_seq : 1,

@@ -106,12 +106,23 @@ __device__ __forceinline__ void load_bias32(const float* bias, int col0, int n, 
 //   RESID                 : 32 increments alpha * (acc + bias) to be ADDED to the fp32 residual stream
 //   QKV                   : pass 0 -> acc + bias (q+u | k | v), pass 1 -> acc + bias2 (q+v; only for col0 < qkv_dp)
 //   GLU                   : 16 values a * sigmoid(g) for output columns col0/2.. (zeroed at padded frames)
+// epi_math: same, with the 32 bias values already in registers (the tensor-core kernels stage a tile's bias in shared
+// memory while they wait for the accumulator: a per-chunk global load is an L1 miss per tile and was measured to be
+// ~300 of the ~650 cycles an epilogue chunk took).
+template <int EPI, bool kFast>
+__device__ __forceinline__ void epi_math(const EpiParams& p, long long out_row, float (&acc)[32], const float (&b)[32]);
+
 template <int EPI, bool kFast>
 __device__ __forceinline__ void epi_compute(const EpiParams& p, long long out_row, int col0, float (&acc)[32],
                                             int pass) {
   const int n = min(32, p.N - col0);
   float b[32];
   load_bias32((EPI == EPI_QKV && pass == 1) ? p.bias2 : p.bias, col0, n, b);
+  epi_math<EPI, kFast>(p, out_row, acc, b);
+}
+
+template <int EPI, bool kFast>
+__device__ __forceinline__ void epi_math(const EpiParams& p, long long out_row, float (&acc)[32], const float (&b)[32]) {
   bool keep = true;
   if constexpr (EPI == EPI_LINEAR || EPI == EPI_SWISH || EPI == EPI_RELU || EPI == EPI_GLU) {
     if (p.lens != nullptr) {

@@ -39,11 +39,12 @@ struct TcParams {
   int conv_fblocks;   // output tiles along frequency (4 bins each)
   int conv_To, conv_Fo;
   int dbg_nofence;  // CFB_GEMM_NOFENCE=1: timing experiment only (results may be stale)
+  long long* trace;  // CFB_GEMM_TRACE=1: per-tile clock marks of CTA 0 (epilogue warp 2, MMA issuer)
   EpiParams ep;
 };
 
 // SBUF = staging boxes per epilogue warp (2 = double-buffered TMA stores; 1 frees 32 KB for one more operand stage)
-template <int BN, int STAGES, int SBUF = (BN == 256 ? 1 : 2)>
+template <int BN, int STAGES, int SBUF = ((BN == 256 && STAGES >= 4) ? 1 : 2)>
 struct SmemLayout {
   static constexpr int kSBuf = SBUF;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -52,7 +53,10 @@ struct SmemLayout {
   static constexpr int kStagingOffset = STAGES * kStageBytes;  // per epilogue warp: 2 buffers x (32 rows x 128 B)
   static constexpr int kStagingBytes = kEpiWarps * SBUF * 4096;
   static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + alignment slack
+  static constexpr int kBiasOffset = kBarOffset + 256;          // float [2][BN]: the current / next tile's bias
+  static constexpr int kNeeded = kBiasOffset + 2 * BN * 4;
+  // operand tiles need 1024-byte alignment; ask for the slack when it fits (the kernel traps if it did not get it)
+  static constexpr int kTotal = kNeeded + 1024 <= 227 * 1024 ? kNeeded + 1024 : 227 * 1024;
 };
 
 template <int BN, int STAGES, int EPI, typename TOut, bool CONV>
@@ -62,6 +66,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (static_cast<int>(smem - smem_raw) + L::kNeeded > L::kTotal) __trap();  // alignment slack did not fit
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;  // [2]
@@ -143,8 +148,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
+        const bool trm = p.trace != nullptr && blockIdx.x == 0 && it < 16;
+        if (trm) p.trace[64 + it * 4 + 0] = clock64();
         ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
+        if (trm) p.trace[64 + it * 4 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
@@ -164,6 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         ptx::tc_commit(&acc_full[buf]);
+        if (trm) p.trace[64 + it * 4 + 2] = clock64();
       }
     }
   } else {
@@ -202,8 +211,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         out_row = static_cast<long long>(m_blk) * kBlockM + row_in_tile;
         row_ok = out_row < p.ep.M;
       }
+      const bool trc = p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 16;
+      if (trc) p.trace[it * 4 + 0] = clock64();
+      // stage this tile's bias (BN floats) in shared memory while the accumulator is still being computed
+      float* bias_s = reinterpret_cast<float*>(smem + L::kBiasOffset) + buf * BN;
+      {
+        const int e = static_cast<int>(threadIdx.x) - 64;
+        if (e < BN) {
+          const int col = n_blk * BN + e;
+          bias_s[e] = (p.ep.bias != nullptr && col < p.ep.N) ? __ldg(p.ep.bias + col) : 0.f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      }
       ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
+      if (trc) p.trace[it * 4 + 1] = clock64();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * BN;
 #pragma unroll 1
       for (int box = half; box < kBoxes; box += kEpiWarps / 4) {
@@ -213,11 +235,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
         for (int pass = 0; pass < n_pass; ++pass) {
           uint8_t* sbuf = stage_base + (L::kSBuf == 2 ? (box_counter & 1u) * 4096 : 0u);
+          const bool trb = trc && it == 2;
+          const int tb0 = 32 + (box >> 1) * 8;
+          if (trb) p.trace[tb0 + 0] = clock64();
           if (lane == 0) {  // the store that last read this buffer has drained it
             if constexpr (L::kSBuf == 2) ptx::bulk_wait_read<1>();
             else ptx::bulk_wait_read<0>();
           }
           __syncwarp();
+          if (trb) p.trace[tb0 + 1] = clock64();
           uint8_t* srow = sbuf + lane * 128;
 #pragma unroll
           for (int ch = 0; ch < kChunks; ++ch) {
@@ -227,7 +253,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float acc[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-            if (row_ok) epi_compute<EPI, kFast>(p.ep, out_row, acc_col0 + ch * 32, acc, pass);
+            if (row_ok) {
+              if (EPI == EPI_QKV && pass == 1) {
+                epi_compute<EPI, kFast>(p.ep, out_row, acc_col0 + ch * 32, acc, pass);  // q + v: bias2 from global
+              } else {
+                float b[32];
+                const float4* bs = reinterpret_cast<const float4*>(bias_s + box * kAccPerBox + ch * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 t = bs[j];
+                  b[4 * j] = t.x, b[4 * j + 1] = t.y, b[4 * j + 2] = t.z, b[4 * j + 3] = t.w;
+                }
+                epi_math<EPI, kFast>(p.ep, out_row, acc, b);
+              }
+            }
             if constexpr (sizeof(TOut) == 4) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -246,8 +285,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          if (trb) p.trace[tb0 + 2] = clock64();
           if (!p.dbg_nofence) ptx::fence_proxy_async_smem();
           __syncwarp();
+          if (trb) p.trace[tb0 + 3] = clock64();
           if (lane == 0) {
             if constexpr (CONV) {
               ptx::tma_store_4d(&tmO, sbuf, acc_col0, cv_f0, cv_t0, cv_b);
@@ -266,11 +307,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             ptx::bulk_commit();
           }
+          if (trb) p.trace[tb0 + 4] = clock64();
           ++box_counter;
         }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&acc_empty[buf]);
+      if (trc) p.trace[it * 4 + 2] = clock64();
     }
     if (lane == 0) ptx::bulk_wait<0>();  // all output writes complete before the CTA retires
   }
@@ -283,6 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+long long* g_gemm_trace = nullptr;
 int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -348,6 +392,8 @@ int dispatch_epi(int epi, bool out_bf16, const CUtensorMap& tmA, const CUtensorM
 
 }  // namespace
 
+long long* g_gemm_trace_view() { return g_gemm_trace; }
+
 int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
   if ((g.lda % 8) || (g.ldw % 8) || (g.K % 8)) {
@@ -379,6 +425,14 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
   p.num_tiles = m_tiles * n_tiles;
   p.num_k_blocks = (g.K + kBlockK - 1) / kBlockK;
   p.dbg_nofence = getenv("CFB_GEMM_NOFENCE") != nullptr;
+  p.trace = nullptr;
+  if (getenv("CFB_GEMM_TRACE")) {
+    if (!g_gemm_trace) {
+      cudaMalloc(&g_gemm_trace, 128 * sizeof(long long));
+    }
+    cudaMemsetAsync(g_gemm_trace, 0, 128 * sizeof(long long), st);
+    p.trace = g_gemm_trace;
+  }
   p.ep = g.ep;
   p.ep.M = g.M;
   p.ep.N = g.N;
@@ -398,7 +452,10 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
     uint32_t box[2] = {f32 ? 32u : 64u, 32u};
     if (!encode_tmap(&tmO, g.ep.out, f32, 2, dims, strides, box, err)) return -1;
   }
-  if (bn == 256) return dispatch_epi<256, 4, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
+  // long K: the mainloop dominates -> 4 operand stages, single-buffered staging; short K: a tile's epilogue takes as
+  // long as its mainloop and a TMA store holds its staging box ~1500 cycles -> 3 stages, double-buffered staging
+  if (bn == 256 && p.num_k_blocks >= 16) return dispatch_epi<256, 4, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
+  if (bn == 256) return dispatch_epi<256, 3, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
   return dispatch_epi<128, 5, false>(g.epi, g.out_bf16, tmA, tmB, tmO, p, st, err);
 }
 
@@ -455,3 +512,10 @@ int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err) {
 }
 
 }  // namespace cfb
+
+// debug: clock marks of the last traced GEMM launch (128 values)
+extern "C" __attribute__((visibility("default"))) int cfb_debug_gemm_trace(long long* host_out) {
+  if (!cfb::g_gemm_trace_view()) return 1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(host_out, cfb::g_gemm_trace_view(), 128 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+}
