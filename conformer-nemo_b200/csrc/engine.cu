@@ -63,6 +63,9 @@ struct cfb_handle {
   Slot sub_w1, sub_b1, sub_w2, sub_b2, sub_w3, sub_b3, w_pos, div_term, w_oproj, b_oproj;
   std::vector<LayerW> layers;
   int launches = 0;
+  // two-stream micro-batching (see cfb_forward): the second half of a batch runs on an auxiliary stream
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   mutable std::string err;
   // optional per-launch event timing
   bool profiling = false;
@@ -137,6 +140,19 @@ Plan make_plan(const cfb_handle* h, int B, int T) {
   }
   p.total = off;
   return p;
+}
+
+// cfb_forward may run a batch as two half-batches on two streams, each half with its own plan
+bool micro_batching_enabled() {
+  static const bool on = !(getenv("CFB_MICROBATCH") != nullptr && atoi(getenv("CFB_MICROBATCH")) == 0);
+  return on;
+}
+int micro_split(const cfb_handle* h, int B) { return (!h->validate && micro_batching_enabled() && B >= 8) ? (B + 1) / 2 : 0; }
+size_t workspace_need(const cfb_handle* h, int B, int T) {
+  size_t need = make_plan(h, B, T).total;
+  const int b0 = micro_split(h, B);
+  if (b0 > 0) need = std::max(need, make_plan(h, b0, T).total + make_plan(h, B - b0, T).total);
+  return need;
 }
 
 const HostTensor* find(const cfb_handle* h, const std::string& key) {
@@ -235,6 +251,13 @@ int cfb_create(const cfb_config* cfg, int device, cfb_handle** out) {
     delete h;
     return bad(CFB_ERR_UNSUPPORTED, "d_ff and feat_out must be multiples of 8");
   }
+  cudaSetDevice(device);
+  if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    delete h;
+    return bad(CFB_ERR_CUDA, "could not create the auxiliary stream / events");
+  }
   *out = h;
   return CFB_OK;
 }
@@ -243,6 +266,9 @@ void cfb_destroy(cfb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->arena) cudaFree(h->arena);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (auto& e : h->ev_pool) cudaEventDestroy(e);
   delete h;
 }
@@ -490,7 +516,7 @@ int cfb_output_frames(const cfb_handle* h, int T, int* t_out) {
 
 int cfb_workspace_bytes(const cfb_handle* h, int B, int T, size_t* out) {
   if (!h || !out || B < 1 || T < 1) return fail(h, CFB_ERR_INVALID_ARG, "cfb_workspace_bytes: bad argument");
-  *out = make_plan(h, B, T).total;
+  *out = workspace_need(h, B, T);
   return CFB_OK;
 }
 
@@ -567,20 +593,13 @@ int cfb_debug_buffer(const cfb_handle* h, int B, int T, const char* name, size_t
   return fail(h, CFB_ERR_INVALID_ARG, "cfb_debug_buffer: unknown buffer " + n);
 }
 
-int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t* lengths, int B, int T, void* encoded,
-                int out_dtype, int32_t* encoded_len, void* workspace, size_t ws_bytes, cfb_stream stream) {
-  if (!h) return CFB_ERR_INVALID_ARG;
-  if (!h->finalized) return fail(h, CFB_ERR_STATE, "cfb_forward: weights are not finalized");
-  if (!feats || !encoded || !encoded_len || !workspace || B < 1 || T < 1)
-    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward: null pointer or empty batch");
-  if (feats_dtype != CFB_F32 && feats_dtype != CFB_BF16)
-    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward: feats must be f32 or bf16");
-  if (out_dtype != CFB_F32 && out_dtype != CFB_BF16)
-    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward: encoded must be f32 or bf16");
+}  // extern "C"
+
+// One contiguous range of the batch on one stream (the whole batch, or one half of it).
+static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, const int64_t* lengths, int B, int T,
+                         void* encoded, int out_dtype, int32_t* encoded_len, void* workspace, cudaStream_t st,
+                         int* launches_out) {
   const Plan pl = make_plan(h, B, T);
-  if (ws_bytes < pl.total || (reinterpret_cast<uintptr_t>(workspace) & 255))
-    return fail(h, CFB_ERR_WORKSPACE, "cfb_forward: workspace too small or not 256-byte aligned");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const bool v = h->validate;
   const bool abf = !v;  // activations / matrices in bf16
@@ -931,8 +950,52 @@ int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t
     CFB_TRY(gemm(a, d, h->w_oproj, d, N, h->d_out, d, EPI_LINEAR, out_dtype == CFB_BF16, ep, "out_proj"), "out_proj");
   }
 #undef CFB_TRY
-  h->launches = launches;
+  *launches_out += launches;
   return CFB_OK;
+}
+
+extern "C" {
+
+int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t* lengths, int B, int T, void* encoded,
+                int out_dtype, int32_t* encoded_len, void* workspace, size_t ws_bytes, cfb_stream stream) {
+  if (!h) return CFB_ERR_INVALID_ARG;
+  if (!h->finalized) return fail(h, CFB_ERR_STATE, "cfb_forward: weights are not finalized");
+  if (!feats || !encoded || !encoded_len || !workspace || B < 1 || T < 1)
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward: null pointer or empty batch");
+  if (feats_dtype != CFB_F32 && feats_dtype != CFB_BF16)
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward: feats must be f32 or bf16");
+  if (out_dtype != CFB_F32 && out_dtype != CFB_BF16)
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward: encoded must be f32 or bf16");
+  if (ws_bytes < workspace_need(h, B, T) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return fail(h, CFB_ERR_WORKSPACE, "cfb_forward: workspace too small or not 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int launches = 0;
+  // Utterances are independent, so a batch can run as two half-batches on two streams (fork / join with events,
+  // capturable): the halves' kernels interleave on the GPU -- one half's memory-bound LayerNorms and kernel tails
+  // overlap the other half's GEMMs instead of leaving the tensor cores idle.  Results are identical to the
+  // single-stream schedule (every row sees the same padded extent T).  Off while per-kernel profiling is on.
+  const int b0 = h->profiling ? 0 : micro_split(h, B);
+  if (b0 == 0) {
+    int rc = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, workspace, st, &launches);
+    h->launches = launches;
+    return rc;
+  }
+  const int b1 = B - b0;
+  const int t_out = conv_out(conv_out(T));
+  const size_t in_es = feats_dtype == CFB_F32 ? 4 : 2, out_es = out_dtype == CFB_F32 ? 4 : 2;
+  const uint8_t* feats1 = reinterpret_cast<const uint8_t*>(feats) + static_cast<size_t>(b0) * h->F0 * T * in_es;
+  uint8_t* enc1 = reinterpret_cast<uint8_t*>(encoded) + static_cast<size_t>(b0) * t_out * h->d_out * out_es;
+  uint8_t* ws1 = reinterpret_cast<uint8_t*>(workspace) + make_plan(h, b0, T).total;
+  if (cudaEventRecord(h->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0) != cudaSuccess)
+    return fail(h, CFB_ERR_CUDA, "cfb_forward: stream fork failed");
+  int rc = forward_range(h, feats, feats_dtype, lengths, b0, T, encoded, out_dtype, encoded_len, workspace, st, &launches);
+  int rc1 = forward_range(h, feats1, feats_dtype, lengths ? lengths + b0 : nullptr, b1, T, enc1, out_dtype, encoded_len + b0,
+                          ws1, h->aux_stream, &launches);
+  // always join, even after an error, so a capture in progress is not left with a dangling branch
+  cudaEventRecord(h->ev_join, h->aux_stream);
+  cudaStreamWaitEvent(st, h->ev_join, 0);
+  h->launches = launches;
+  return rc != CFB_OK ? rc : rc1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -204,3 +204,59 @@ def test_enable_cuda_graphs_matches_eager_and_tracks_shapes():
     enc.enable_cuda_graphs(False)
     y, _ = enc(audio_signal=cases[0][0], length=cases[0][1])
     assert float((y - eager[0][0]).abs().max()) == 0.0
+
+
+def test_two_stream_micro_batching_is_bit_identical_to_separate_halves():
+    """B >= 8: cfb_forward runs the batch as two half-batches on two streams (fork / join).  Utterances are independent
+    and both halves see the same padded extent T, so the result must equal running the halves as separate calls bit
+    for bit, encoded_len included -- eagerly and under graph replay."""
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=2, d_model=256, n_heads=4)
+    sd = oc.random_state_dict(cfg, 53)
+    lens = [400, 333, 17, 256, 399, 1, 120, 64, 400, 250, 77]
+    x, length = oc.synthetic_batch(len(lens), 80, 400, lens, seed=31)
+    enc = build(cfg, sd, "bf16")
+    xs, ls = x.cuda(), length.cuda()
+    y, ylen = enc(audio_signal=xs, length=ls)
+    torch.cuda.synchronize()
+    b0 = (len(lens) + 1) // 2
+    ya, la = (t.clone() for t in enc(audio_signal=xs[:b0].contiguous(), length=ls[:b0].contiguous()))  # B < 8: one stream
+    yb, lb = (t.clone() for t in enc(audio_signal=xs[b0:].contiguous(), length=ls[b0:].contiguous()))
+    torch.cuda.synchronize()
+    assert torch.equal(ylen, torch.cat([la, lb]))
+    assert float((y - torch.cat([ya, yb])).abs().max()) == 0.0
+    want, want_len = oc.encoder_forward(sd, cfg, x, length)
+    assert torch.equal(ylen.cpu(), want_len)
+    st = compare(y.cpu(), want, ylen)
+    assert st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, st
+    enc.enable_cuda_graphs(True)
+    for _ in range(2):
+        yg, lg = enc(audio_signal=xs, length=ls)
+        torch.cuda.synchronize()
+        assert torch.equal(lg, ylen) and float((yg - y).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_random_shapes_and_lengths_against_oracle(seed):
+    """Seeded sweep over the shapes the kernels special-case: d_model 176 / 256 / 512 (head dims 44 / 64 / 32), batch
+    sizes on both sides of the micro-batching threshold, T not a multiple of anything, utterances from 1 frame to full
+    length, subsampling_conv_channels != d_model, feat_out projection."""
+    rnd = np.random.RandomState(100 + seed)
+    d_model, heads = [(176, 4), (256, 4), (512, 8), (256, 8), (512, 16), (176, 4)][seed]
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=2, d_model=d_model, n_heads=heads,
+                           subsampling_conv_channels=[-1, 64, -1, 128, -1, 176][seed],
+                           feat_out=[-1, -1, 320, -1, -1, 128][seed])
+    sd = oc.random_state_dict(cfg, 60 + seed)
+    b = int(rnd.choice([1, 3, 8, 11]))
+    t = int(rnd.randint(9, 700))
+    lens = [int(v) for v in rnd.randint(1, t + 1, size=b)]
+    lens[int(rnd.randint(0, b))] = t
+    x, length = oc.synthetic_batch(b, 80, t, lens, seed=70 + seed)
+    want, want_len = oc.encoder_forward(sd, cfg, x, length)
+    enc = build(cfg, sd, "bf16")
+    y, ylen = enc(audio_signal=x.cuda(), length=length.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(ylen.cpu(), want_len), (lens, ylen, want_len)
+    st = compare(y.cpu(), want, ylen)
+    assert st["nan"] == 0 and st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, (st, cfg, b, t, lens)
+    for row, n in enumerate(want_len.tolist()):  # frames past encoded_len are written as zeros
+        assert float(y[row, :, n:].abs().max()) == 0.0 if n < y.shape[2] else True
