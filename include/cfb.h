@@ -188,6 +188,17 @@ CFB_API int cfb_op_rel_attention(int use_tensor_cores, const void* qkv, const vo
 /* encoded_len = calc_length(lengths) repeated n_stages times (subsampling.py:272-282), float32 arithmetic inside. */
 CFB_API int cfb_op_lengths(const int64_t* lengths, int32_t* out, int B, int T_full, int n_stages, cfb_stream stream);
 
+/* ---- CTC head on the encoder output (the caller right after the path) -----------------------
+ * ConvASRDecoder (modules/conv_asr.py:437-444): logprobs = log_softmax(x W^T + b) over the V+1 classes, and the greedy
+ * argmax the CTC models take next (models/ctc_models.py:593-594).
+ *   x        (M, d) rows = frames (the contiguous (B, T', d) encoder output), CFB_F32 or CFB_BF16
+ *   W        (v1, d) bf16 row-major = decoder_layers.0.weight[:, :, 0];  bias (v1) fp32
+ *   logprobs (M, v1) fp32;  best (M) int32 = argmax over classes (first index on ties), may be NULL
+ *   scratch  >= cfb_ctc_head_scratch_bytes(M, d, v1), 256-byte aligned.  Enqueue-only on `stream`. */
+CFB_API size_t cfb_ctc_head_scratch_bytes(int M, int d, int v1);
+CFB_API int cfb_op_ctc_head(const void* x, int x_dtype, const void* W, const float* bias, int M, int d, int v1,
+                    float* logprobs, int32_t* best, void* scratch, size_t scratch_bytes, cfb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

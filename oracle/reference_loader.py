@@ -98,3 +98,18 @@ def build_reference_encoder(cfg, state_dict=None):
         missing = [m for m in missing if "num_batches_tracked" not in m]
         assert not missing and not unexpected, (missing, unexpected)
     return enc.eval()
+
+
+def load_reference_ctc_decoder_class():
+    """Returns the reference ``ConvASRDecoder`` class (modules/conv_asr.py:397), loaded unmodified.  conv_asr.py
+    imports omegaconf (absent here) only for type names; an inert stand-in is registered for it."""
+    load_reference_encoder_class()  # registers the stub packages
+    if "omegaconf" not in sys.modules:
+        om = types.ModuleType("omegaconf")
+        om.MISSING = "???"
+        om.ListConfig = list
+        om.DictConfig = dict
+        om.OmegaConf = type("OmegaConf", (), {})
+        sys.modules["omegaconf"] = om
+    mod = importlib.import_module("nemo.collections.asr.modules.conv_asr")
+    return mod.ConvASRDecoder

@@ -1,0 +1,121 @@
+"""CTC head: oracle vs the reference's golden vectors and host logic on CPU; the CUDA head
+(through cfb_op_ctc_head) against the oracle on the GPU."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import conformer_nemo_b200 as cn
+from oracle import ctc_head_oracle as ho
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "ctc_head_*.npz")))
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    x = torch.from_numpy(z["encoder_output"])
+    v = int(z["num_classes"])
+    if "weight" in z.files:
+        sd = {"decoder_layers.0.weight": torch.from_numpy(z["weight"]), "decoder_layers.0.bias": torch.from_numpy(z["bias"])}
+    else:
+        sd = ho.random_head_state_dict(x.shape[1], v, int(z["weight_seed"]))
+    assert abs(float(sd["decoder_layers.0.weight"].double().sum()) - float(z["weight_checksum"])) < 1e-6
+    return x, v, sd, torch.from_numpy(z["log_probs"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    x, v, sd, want = load(name)
+    got = ho.ctc_head_forward(sd, x)
+    assert got.shape == want.shape == (x.shape[0], x.shape[2], v + 1)
+    assert float((got - want).abs().max()) <= 2e-6
+
+
+def test_oracle_matches_live_reference_when_mounted():
+    from oracle import reference_loader as rl
+
+    if not rl.reference_available():
+        pytest.skip("reference tree not mounted")
+    cls = rl.load_reference_ctc_decoder_class()
+    sd = ho.random_head_state_dict(64, 40, 9)
+    dec = cls(feat_in=64, num_classes=40)
+    dec.load_state_dict(sd, strict=True)
+    x = torch.randn(2, 64, 19, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        want = dec(encoder_output=x)
+    assert float((ho.ctc_head_forward(sd, x) - want).abs().max()) == 0.0
+
+
+def test_greedy_collapse_cases():
+    blank = 4
+    pred = torch.tensor([[1, 1, 4, 1, 2, 2, 4, 4, 3, 3], [4, 4, 4, 4, 4, 4, 4, 4, 4, 4], [0, 0, 0, 1, 4, 0, 2, 2, 2, 2]])
+    assert ho.greedy_collapse(pred, [10, 10, 10], blank) == [[1, 1, 2, 3], [], [0, 1, 0, 2]]
+    assert ho.greedy_collapse(pred, [3, 0, 4], blank) == [[1], [], [0, 1]]
+    assert cn.ctc_greedy_decode(pred, torch.tensor([3, 0, 4]), blank) == ho.greedy_collapse(pred, [3, 0, 4], blank)
+    assert cn.ctc_greedy_decode(pred, None, blank) == ho.greedy_collapse(pred, None, blank)
+
+
+def test_decoder_surface_matches_reference():
+    dec = cn.ConvASRDecoder(feat_in=176, num_classes=28)
+    assert {k: tuple(v.shape) for k, v in dec.state_dict().items()} == {
+        "decoder_layers.0.weight": (29, 176, 1), "decoder_layers.0.bias": (29,)}
+    with pytest.raises(ValueError):
+        cn.ConvASRDecoder(feat_in=176, num_classes=-1)
+    with pytest.raises(ValueError):
+        cn.ConvASRDecoder(feat_in=176, num_classes=3, vocabulary=["a", "b"])
+    dec = cn.ConvASRDecoder(feat_in=176, num_classes=-1, vocabulary=list("abc"))
+    assert dec.num_classes_with_blank == 4 and dec.vocabulary == ["a", "b", "c"]
+    with pytest.raises(RuntimeError):  # no CPU path
+        dec(encoder_output=torch.zeros(1, 176, 5))
+
+
+def assert_argmax_agrees(pred, want):
+    """Greedy agreement >= 99 % (BASELINE.json north_star); a disagreement is only tolerated where the reference's own
+    margin between the two classes is inside the bf16 tolerance (random-init heads have many near-ties)."""
+    ref = want.argmax(-1)
+    margin = want.gather(-1, ref.unsqueeze(-1)).squeeze(-1) - want.gather(-1, pred.unsqueeze(-1)).squeeze(-1)
+    assert float(margin.max()) <= 0.1, float(margin.max())
+    assert float((pred == ref).float().mean()) >= (0.99 if pred.numel() >= 1000 else 0.95)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_cuda_head_matches_golden(name):
+    x, v, sd, want = load(name)
+    dec = cn.ConvASRDecoder(feat_in=x.shape[1], num_classes=v)
+    dec.load_state_dict(sd)
+    dec = dec.cuda()
+    lp, pred = dec.forward_with_predictions(x.cuda())
+    torch.cuda.synchronize()
+    assert lp.shape == want.shape and pred.shape == want.shape[:2]
+    assert torch.isfinite(lp).all()
+    assert float((lp.cpu() - want).abs().max()) <= 5e-2              # bf16 operands, fp32 accumulation + log_softmax
+    assert float((lp.exp().sum(-1) - 1).abs().max()) <= 1e-4
+    assert torch.equal(pred, lp.argmax(-1))                            # the kernel's argmax == torch's on its own output
+    assert_argmax_agrees(pred.cpu(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,t,d,v,dtype", [(32, 500, 512, 1024, torch.float32), (4, 333, 256, 128, torch.bfloat16),
+                                          (1, 1, 176, 28, torch.float32), (3, 77, 512, 5000, torch.float32)])
+def test_cuda_head_matches_oracle_on_encoder_like_input(b, t, d, v, dtype):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(b, t, d, generator=g)                             # contiguous (B, T, D): what the encoder hands over
+    sd = ho.random_head_state_dict(d, v, 11)
+    dec = cn.ConvASRDecoder(feat_in=d, num_classes=v)
+    dec.load_state_dict(sd)
+    dec = dec.cuda()
+    xin = x.to(dtype).cuda().transpose(1, 2)
+    lp, pred = dec.forward_with_predictions(xin)
+    want = ho.ctc_head_forward(sd, x.to(dtype).float().transpose(1, 2))
+    torch.cuda.synchronize()
+    err = (lp.cpu() - want).abs()
+    assert float(err.max()) <= 5e-2, float(err.max())
+    assert_argmax_agrees(pred.cpu(), want)
+    lens = [t] * b
+    got = cn.ctc_greedy_decode(pred, lens, v)
+    ref = ho.greedy_collapse(lp.argmax(-1).cpu(), lens, v)
+    assert got == ref
