@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         int frames_per_seq) {
   // Grid-stride over rows, one warp per row: the NEXT row's loads are issued before the current row is reduced, so a
   // warp always has a full row (2 KB at d = 512) in flight and blocks are not re-launched every eight rows.
+  // A lane owns PAIRS of adjacent float4 (8 consecutive columns): 32-byte loads, one 16-byte store for bf16 outputs.
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -61,11 +62,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   constexpr int kN = NV > 0 ? NV : kMaxVec;
   const int nvec = d >> 2;  // float4 per row
   const float inv_d = 1.0f / static_cast<float>(d);
+  // float4 index of slot k: pair p = k / 2 covers float4 [64 p + 2 lane, 64 p + 2 lane + 1]
+  auto vidx = [&](int k) { return 64 * (k >> 1) + 2 * lane + (k & 1); };
   float4 g[kN], b[kN];
 #pragma unroll
   for (int k = 0; k < kN; ++k) {
-    const int i = lane + 32 * k;
-    if (NV > 0 || i < nvec) {
+    const int i = vidx(k);
+    if (i < nvec) {
       g[k] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
       b[k] = __ldg(reinterpret_cast<const float4*>(beta) + i);
     }
@@ -75,8 +78,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(r) * d);
 #pragma unroll
     for (int k = 0; k < kN; ++k) {
-      const int i = lane + 32 * k;
-      if (NV > 0 || i < nvec) nx[k] = __ldg(xr + i);
+      const int i = vidx(k);
+      if (i < nvec) nx[k] = __ldg(xr + i);
     }
   };
   fetch(row);
@@ -95,27 +98,31 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     }
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kN; ++k) {
-      const int i = lane + 32 * k;
-      if (NV > 0 || i < nvec) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-    }
+    for (int k = 0; k < kN; ++k)
+      if (vidx(k) < nvec) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
     const float mean = warp_sum(s) * inv_d;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < kN; ++k) {
-      const int i = lane + 32 * k;
-      if (NV > 0 || i < nvec) {
+    for (int k = 0; k < kN; ++k)
+      if (vidx(k) < nvec) {
         v[k].x -= mean, v[k].y -= mean, v[k].z -= mean, v[k].w -= mean;
         q += (v[k].x * v[k].x + v[k].y * v[k].y) + (v[k].z * v[k].z + v[k].w * v[k].w);
       }
-    }
     const float rstd = 1.0f / sqrtf(warp_sum(q) * inv_d + 1e-5f);
 #pragma unroll
-    for (int k = 0; k < kN; ++k) {
-      const int i = lane + 32 * k;
-      if (NV > 0 || i < nvec) {
-        store4(orow + 4 * i, fmaf(v[k].x * rstd, g[k].x, b[k].x), fmaf(v[k].y * rstd, g[k].y, b[k].y),
-               fmaf(v[k].z * rstd, g[k].z, b[k].z), fmaf(v[k].w * rstd, g[k].w, b[k].w));
+    for (int k = 0; k < kN; k += 2) {
+      const int i = vidx(k);
+      float r8[8];
+      r8[0] = fmaf(v[k].x * rstd, g[k].x, b[k].x), r8[1] = fmaf(v[k].y * rstd, g[k].y, b[k].y);
+      r8[2] = fmaf(v[k].z * rstd, g[k].z, b[k].z), r8[3] = fmaf(v[k].w * rstd, g[k].w, b[k].w);
+      if (k + 1 < kN) {
+        r8[4] = fmaf(v[k + 1].x * rstd, g[k + 1].x, b[k + 1].x), r8[5] = fmaf(v[k + 1].y * rstd, g[k + 1].y, b[k + 1].y);
+        r8[6] = fmaf(v[k + 1].z * rstd, g[k + 1].z, b[k + 1].z), r8[7] = fmaf(v[k + 1].w * rstd, g[k + 1].w, b[k + 1].w);
+      }
+      if (k + 1 < kN && i + 1 < nvec) {
+        store8(orow + 4 * i, r8);
+      } else if (i < nvec) {
+        store4(orow + 4 * i, r8[0], r8[1], r8[2], r8[3]);
       }
     }
   }
