@@ -205,11 +205,13 @@ def algorithmic_costs(kw, batches):
         add(by, "norm_conv", L * n * d * 6)
         add(by, "norm_out", (L - 1) * n * d * 10 + n * d * 8)  # reads x, writes x (fp32) + the next bf16 operand
         add(by, "depthwise conv", L * (n * d * 4 + 31 * d * 4))
+        # fused conv-module tail (conv_tail.cu): g (bf16) in, x (fp32) read + write; 2*n*d*d FLOPs need less time
+        add(by, "depthwise+pointwise_conv2", L * (n * d * 10 + 32 * d * 4 + d * d * 2))
     return fl, by
 
 
 GEMM_LABELS = ["pre_encode.out", "linear_pos", "qkv projection", "linear_out", "pointwise_conv1+glu", "pointwise_conv2",
-               "linear1+swish", "linear2"]
+               "linear1+swish", "linear2"]  # the fused depthwise+pointwise_conv2 kernel is not gemm_tc_kernel: reported apart
 
 
 def build_batches(args, kw, rank, world):

@@ -164,4 +164,22 @@ bool encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64
 bool encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
                  const uint64_t* strides_bytes, const uint32_t* box, std::string* err);
 
+// same with the shared-memory swizzle chosen by the caller (false = rows land densely, for tiles read by SIMT code)
+bool encode_tmap_ex(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, std::string* err);
+
+// depth-wise conv (+ folded BatchNorm + Swish) fused into pointwise_conv2 and the residual update (conv_tail.cu):
+//   x[b,t,:] += W2 * swish(bias_dw + sum_k taps[k] * g[b, t + k - 15, :]) + bias2
+// taps32: (32, d) fp32, rows 0..30 = the 31 taps (shorter kernels centred, zero padded), row 31 = the folded bias
+struct DwPwDesc {
+  const void* g = nullptr;      // (B*T, d) bf16, GLU output with padded frames zeroed
+  const float* taps32 = nullptr;
+  const void* W = nullptr;      // (d, d) bf16 pointwise_conv2 weight
+  const float* bias2 = nullptr; // (d)
+  float* x = nullptr;           // (B*T, d) fp32 residual stream, updated in place
+  int B = 0, T = 0, d = 0;
+};
+bool dw_pw_supported(int d);
+int launch_dw_pw(const DwPwDesc& c, cudaStream_t st, std::string* err);
+
 }  // namespace cfb

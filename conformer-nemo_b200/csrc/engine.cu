@@ -40,7 +40,7 @@ struct LayerW {
   Slot ln_g[5], ln_b[5];
   Slot ff_w1[2], ff_b1[2], ff_w2[2], ff_b2[2];
   Slot w_qkv, b_qkv, b_qv, w_out, b_out;
-  Slot w_pw1, b_pw1, dw_taps, dw_bias, w_pw2, b_pw2;
+  Slot w_pw1, b_pw1, dw_taps, dw_bias, dw_taps32, w_pw2, b_pw2;
 };
 
 std::string g_create_error;
@@ -482,6 +482,14 @@ int cfb_finalize_weights(cfb_handle* h) {
       }
       lw.dw_taps = ab.put_f32(taps);
       lw.dw_bias = ab.put_f32(bias);
+      {
+        // (32, d) block for the fused depthwise + pointwise_conv2 kernel (conv_tail.cu): 31 centred taps + the bias row
+        std::vector<float> t32(static_cast<size_t>(32) * d, 0.f);
+        const int shift = 15 - (ks - 1) / 2;
+        for (int k = 0; k < ks; ++k) memcpy(&t32[static_cast<size_t>(k + shift) * d], &taps[static_cast<size_t>(k) * d], d * 4);
+        memcpy(&t32[static_cast<size_t>(31) * d], bias.data(), d * 4);
+        lw.dw_taps32 = ab.put_f32(t32);
+      }
       lw.w_pw2 = ab.put_mat(p2w->data, f32);
       lw.b_pw2 = ab.put_f32(p2b->data);
     }
@@ -598,7 +606,7 @@ int cfb_debug_buffer(const cfb_handle* h, int B, int T, const char* name, size_t
 // One contiguous range of the batch on one stream (the whole batch, or one half of it).
 static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, const int64_t* lengths, int B, int T,
                          void* encoded, int out_dtype, int32_t* encoded_len, void* workspace, cudaStream_t st,
-                         int* launches_out) {
+                         int* launches_out, int B_total) {
   const Plan pl = make_plan(h, B, T);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const bool v = h->validate;
@@ -669,7 +677,22 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
   // Row-complete GEMM with the residual update and the following LayerNorm(s) in its epilogue (gemm_ln.cu): the
   // product path for d_model <= 512.  ln1 / ln2 index lw.ln_g / lw.ln_b of the given layers (-1 = none).
   static const bool fused_env = getenv("CFB_FUSED_LN") != nullptr && atoi(getenv("CFB_FUSED_LN")) != 0;
-  const bool fused_ln = fused_env && !v && d <= 512;  // experimental: measured slower than GEMM + LayerNorm (gemm_ln.cu)
+  const bool fused_ln = fused_env && !v && d <= 512;
+  // conv-module tail as one kernel (conv_tail.cu) whenever the shape allows it; CFB_FUSED_TAIL=0 keeps the two launches
+  const char* tail_var = getenv("CFB_FUSED_TAIL");  // 0 = never, 2 = whenever the shape allows, unset = heuristic
+  const bool tail_env = !(tail_var != nullptr && atoi(tail_var) == 0);
+  // One CTA per 128 frames of a sequence: worth it when the CTAs of the whole batch (both micro-batch halves run
+  // concurrently) fill most of the machine; a CTA takes ~29 us however few there are (measured r02f: 128 CTAs 29 us
+  // vs 39 us for the two kernels, 59 CTAs 29 us vs 25 us).
+  bool fused_tail = tail_env && !v && dw_pw_supported(d);
+  if (fused_tail && !(tail_var != nullptr && atoi(tail_var) == 2)) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (sms <= 0) sms = 148;
+    const long long ctas = static_cast<long long>(B_total) * ((T2 + 127) / 128);
+    const long long waves = (ctas + sms - 1) / sms;
+    fused_tail = ctas * 100 >= waves * sms * 65;
+  }  // experimental: measured slower than GEMM + LayerNorm (gemm_ln.cu)
   auto gemm_ln = [&](const void* A, long long lda, const Slot& W, long long ldw, int K, const Slot& bias, float alpha,
                      bool resid, const LayerW* l1, int i1, const LayerW* l2, int i2, float* out_f32, void* out_bf16,
                      long long ld_out, bool mask) -> int {
@@ -890,6 +913,20 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
         eg.lens = lens;
         eg.frames_per_seq = T2;
         CFB_TRY(gemm(a, d, lw.w_pw1, d, N, 2 * d, d, EPI_GLU, abf, eg, "pointwise_conv1+glu"), "pointwise_conv1+glu");
+        if (fused_tail) {
+          // depthwise + BatchNorm + Swish + pointwise_conv2 + residual in one kernel (conv_tail.cu)
+          DwPwDesc dp;
+          dp.g = ws + pl.g;
+          dp.taps32 = h->at<float>(lw.dw_taps32);
+          dp.W = h->arena + lw.w_pw2.off;
+          dp.bias2 = h->at<float>(lw.b_pw2);
+          dp.x = x;
+          dp.B = B;
+          dp.T = T2;
+          dp.d = d;
+          CFB_TRY(launch_dw_pw(dp, st, &err), "depthwise+pointwise_conv2");
+          ++launches;
+        } else {
         CFB_TRY(launch_depthwise(ws + pl.g, h->at<float>(lw.dw_taps), h->at<float>(lw.dw_bias), ws + pl.c, abf, B, T2,
                                  d, h->ksize, st),
                 "depthwise conv");
@@ -900,6 +937,7 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
         e2.ldo = d;
         e2.alpha = 1.f;
         CFB_TRY(gemm(ws + pl.c, d, lw.w_pw2, d, N, d, d, EPI_RESID, false, e2, "pointwise_conv2"), "pointwise_conv2");
+        }
       }
       const int ln = f == 0 ? 0 : 3;
       if (!(f == 0 && l > 0 && abf)) {  // bf16 path: norm_feed_forward1 of layers > 0 is fused into the previous norm_out
@@ -976,7 +1014,7 @@ int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t
   // single-stream schedule (every row sees the same padded extent T).  Off while per-kernel profiling is on.
   const int b0 = h->profiling ? 0 : micro_split(h, B);
   if (b0 == 0) {
-    int rc = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, workspace, st, &launches);
+    int rc = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, workspace, st, &launches, B);
     h->launches = launches;
     return rc;
   }
@@ -988,9 +1026,9 @@ int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t
   uint8_t* ws1 = reinterpret_cast<uint8_t*>(workspace) + make_plan(h, b0, T).total;
   if (cudaEventRecord(h->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0) != cudaSuccess)
     return fail(h, CFB_ERR_CUDA, "cfb_forward: stream fork failed");
-  int rc = forward_range(h, feats, feats_dtype, lengths, b0, T, encoded, out_dtype, encoded_len, workspace, st, &launches);
+  int rc = forward_range(h, feats, feats_dtype, lengths, b0, T, encoded, out_dtype, encoded_len, workspace, st, &launches, B);
   int rc1 = forward_range(h, feats1, feats_dtype, lengths ? lengths + b0 : nullptr, b1, T, enc1, out_dtype, encoded_len + b0,
-                          ws1, h->aux_stream, &launches);
+                          ws1, h->aux_stream, &launches, B);
   // always join, even after an error, so a capture in progress is not left with a dangling branch
   cudaEventRecord(h->ev_join, h->aux_stream);
   cudaStreamWaitEvent(st, h->ev_join, 0);
@@ -1108,6 +1146,22 @@ int cfb_op_depthwise(const void* x, const float* taps, const float* bias, void* 
                      int ksize, cfb_stream stream) {
   int rc = launch_depthwise(x, taps, bias, out, dtype == CFB_BF16, B, T, d, ksize, reinterpret_cast<cudaStream_t>(stream));
   return rc == 0 ? CFB_OK : op_fail(rc, rc == -1 ? "depthwise: ksize must be odd <= 31 and d even" : "");
+}
+
+int cfb_op_dw_pw2(const void* g, const float* taps32, const void* W, const float* bias2, float* x, int B, int T, int d,
+                  cfb_stream stream) {
+  DwPwDesc c;
+  c.g = g;
+  c.taps32 = taps32;
+  c.W = W;
+  c.bias2 = bias2;
+  c.x = x;
+  c.B = B;
+  c.T = T;
+  c.d = d;
+  std::string err;
+  int rc = launch_dw_pw(c, reinterpret_cast<cudaStream_t>(stream), &err);
+  return rc == 0 ? CFB_OK : op_fail(rc, err);
 }
 
 int cfb_op_rel_attention(int use_tc, const void* qkv, const void* pos, int64_t ld_pos, void* ctx, const int32_t* lens,

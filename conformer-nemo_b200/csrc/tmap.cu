@@ -32,6 +32,11 @@ bool encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64
 
 bool encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
                  const uint64_t* strides_bytes, const uint32_t* box, std::string* err) {
+  return encode_tmap_ex(map, base, is_f32, rank, dims, strides_bytes, box, true, err);
+}
+
+bool encode_tmap_ex(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, std::string* err) {
   // A forward pass re-encodes the same few hundred descriptors on every call (same workspace, same shapes); the
   // driver call costs ~1-2 us each, which is visible at 260 launches per forward.  Per-thread cache, no locking.
   struct Key {
@@ -55,7 +60,7 @@ bool encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, cons
   memset(&key, 0, sizeof(key));
   key.base = base;
   key.rank = rank;
-  key.f32 = is_f32 ? 1 : 0;
+  key.f32 = (is_f32 ? 1 : 0) | (swizzle128 ? 0 : 2);
   for (int i = 0; i < rank; ++i) {
     key.dims[i] = dims[i];
     key.box[i] = box[i];
@@ -82,7 +87,8 @@ bool encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, cons
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   CUresult r = g_encode(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
-                        gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) {

@@ -175,6 +175,15 @@ CFB_API int cfb_op_layernorm(const float* x, const float* gamma, const float* be
 CFB_API int cfb_op_depthwise(const void* x, const float* taps, const float* bias, void* out, int dtype, int B, int T, int d,
                      int ksize, cfb_stream stream);
 
+/* Tail of the convolution module in one kernel (conformer_modules.py:168-180 + the residual add of :114):
+ *   x[b,t,:] += W2 * swish(taps32[31] + sum_k taps32[k] * g[b, t + k - 15, :]) + bias2
+ * g (B, T, d) bf16 (GLU output, padded frames zeroed); taps32 (32, d) fp32 = 31 BatchNorm-folded taps (shorter kernels
+ * centred and zero padded) + the folded bias as row 31; W2 (d, d) bf16 = pointwise_conv2.weight; bias2 (d) fp32;
+ * x (B, T, d) fp32, updated in place.  d must be a multiple of 64 and <= 512.  Bit-identical to cfb_op_depthwise
+ * followed by cfb_op_gemm(CFB_EPI_RESID). */
+CFB_API int cfb_op_dw_pw2(const void* g, const float* taps32, const void* W2, const float* bias2, float* x, int B, int T,
+                  int d, cfb_stream stream);
+
 /* Relative-position multi-head attention core (multi_head_attention.py:195-210 + :104-113), everything between the
  * q/k/v projections and linear_out:
  *   qkv  (B*T, 4*Dp): [q+u | q+v | k | v], head h at columns h*dkp .. h*dkp+dk-1 of each part (Dp = H*dkp)

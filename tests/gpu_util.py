@@ -116,3 +116,19 @@ def describe_mismatch(got, want, tol):
     rows = bad.any(1).nonzero().flatten().tolist()
     cols = bad.any(0).nonzero().flatten().tolist()
     return f" bad rows {rows[:12]}..({len(rows)}) bad cols {cols[:12]}..({len(cols)}) frac {float(bad.float().mean()):.4f}"
+
+
+def op_dw_pw2(g, taps, bias, W2, bias2, x):
+    """Fused conv-module tail (cfb_op_dw_pw2).  g (B,T,d) bf16; taps (d, ksize) like depthwise_conv.weight with the
+    BatchNorm already folded; bias (d); W2 (d,d) bf16; bias2 (d); x (B,T,d) fp32 updated in place."""
+    lib = _lib.load_library()
+    B, T, d = g.shape
+    k = taps.shape[1]
+    t32 = torch.zeros(32, d, dtype=torch.float32, device=g.device)
+    sh = 15 - (k - 1) // 2
+    t32[sh:sh + k] = taps.t()
+    t32[31] = bias
+    rc = lib.cfb_op_dw_pw2(ptr(g), ptr(t32), ptr(W2), ptr(bias2), ptr(x), B, T, d, stream())
+    assert rc == 0, _lib.last_error(None)
+    torch.cuda.synchronize()
+    return x

@@ -260,3 +260,27 @@ def test_random_shapes_and_lengths_against_oracle(seed):
     assert st["nan"] == 0 and st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, (st, cfg, b, t, lens)
     for row, n in enumerate(want_len.tolist()):  # frames past encoded_len are written as zeros
         assert float(y[row, :, n:].abs().max()) == 0.0 if n < y.shape[2] else True
+
+
+@pytest.mark.parametrize("name", ["large_d512", "char_d256", "tiny_d64"])
+def test_fused_conv_tail_is_bit_identical_to_the_two_kernel_path(name, monkeypatch):
+    """csrc/conv_tail.cu (depth-wise conv + pointwise_conv2 + residual in one kernel) is chosen by an occupancy
+    heuristic; CFB_FUSED_TAIL=2 forces it, =0 forbids it.  Same arithmetic in the same order: identical bits, and
+    both stay inside the golden tolerance."""
+    z, cfg, sd = load_case(name)
+    enc = build(cfg, sd, "bf16")
+    x = torch.from_numpy(z["audio_signal"]).cuda()
+    length = torch.from_numpy(z["length"]).cuda() if bool(z["has_length"]) else None
+    monkeypatch.setenv("CFB_FUSED_TAIL", "2")
+    y_fused, ylen = enc(audio_signal=x, length=length)
+    n_fused = enc.last_launch_count()
+    torch.cuda.synchronize()
+    y_fused = y_fused.clone()
+    monkeypatch.delenv("CFB_FUSED_TAIL")
+    y_auto, _ = enc(audio_signal=x, length=length)
+    n_auto = enc.last_launch_count()
+    torch.cuda.synchronize()
+    assert n_fused == n_auto - cfg.n_layers, (n_fused, n_auto)  # one launch fewer per layer (tiny batches: auto = split)
+    assert torch.equal(y_fused, y_auto)
+    st = compare(y_fused.float().cpu(), torch.from_numpy(z["encoded"]), ylen)
+    assert st["nan"] == 0 and st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, st

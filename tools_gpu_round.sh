@@ -4,7 +4,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 if [[ "$2" != "notests" ]]; then
-for f in test_gpu_gemm test_gpu_gemm_ln test_gpu_elementwise test_gpu_attention test_gpu_encoder; do
+for f in test_gpu_conv_tail test_gpu_gemm test_gpu_gemm_ln test_gpu_elementwise test_gpu_attention test_gpu_encoder test_ctc_head; do
   echo "=== $f"; timeout 700 python -m pytest tests/$f.py -q -m gpu --tb=short -p no:cacheprovider 2>&1 | tail -40 | tee gpurun_out/${TAG}_$f.log
 done
 fi
