@@ -79,7 +79,7 @@ struct GemmLnDesc {
 };
 int launch_gemm_ln(const GemmLnDesc& g, cudaStream_t st, std::string* err);
 
-// GEMM whose A operand is LayerNorm(x) produced in shared memory by a prologue and kept resident (gemm_lna.cu):
+// GEMM whose A operand is LayerNorm(x), produced by a prologue and kept resident in tensor memory (gemm_lnt.cu):
 //   [y = LN1(x) -> x_out (fp32)]  optional;  a = bf16(LN2(y or x));  D = a W^T with the EPI_SWISH / QKV / GLU / LINEAR
 //   epilogue (bf16 output).  K = d <= 512.
 struct GemmLnaDesc {
@@ -96,7 +96,7 @@ struct GemmLnaDesc {
   int epi = EPI_LINEAR;
   EpiParams ep;
 };
-int launch_gemm_lna(const GemmLnaDesc& g, cudaStream_t st, std::string* err);
+int launch_gemm_lnt(const GemmLnaDesc& g, cudaStream_t st, std::string* err);
 
 struct AttnDesc {
   const void* qkv = nullptr;  // (B*T, 4*Dp)
@@ -137,6 +137,9 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 
 // ---- launchers (each returns a cudaError_t-compatible int; 0 = success) ------------------------------------------
 int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err);
+// CTA-pair (cta_group::2) variant for N % 256 == 0 (gemm_tc2.cu); launch_gemm_tc picks it by shape / CFB_GEMM_2CTA
+bool gemm_tc2_supported(const GemmDesc& g);
+int launch_gemm_tc2(const GemmDesc& g, cudaStream_t st, std::string* err);
 long long* g_gemm_trace_view();
 int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err);
 int launch_gemm_simt(const GemmDesc& g, float* scratch, cudaStream_t st, std::string* err);
@@ -155,6 +158,10 @@ int launch_pos_table(void* out, bool out_bf16, const float* div_term, int T, int
 // first strided conv (1 -> C channels) + ReLU from (B, F, T) features into the parity-split channels-last layout
 int launch_subsample_first(const void* feats, bool feats_bf16, const float* w9, const float* bias, void* y_out,
                            bool out_bf16, int B, int F, int T, int C, int T1, int F1, int Th, int Fh, cudaStream_t st);
+// tensor-core form of the first conv: rows [x_hi(9) | x_lo(9) | 1 | 1 | 0 x 4] (bf16, 24 columns) in y1's row order
+constexpr int kConv0Cols = 24;
+int launch_conv0_im2col(const void* feats, bool feats_bf16, void* a0, int B, int F, int T, int T1, int F1, int Th, int Fh,
+                        cudaStream_t st);
 // validation path: gather the 3x3/s2 patches of a parity-split tensor into a dense (rows x 9*C) fp32 matrix
 int launch_im2col(const float* y_in, float* cols, int B, int C, int Th, int Fh, int To, int Fo, cudaStream_t st);
 

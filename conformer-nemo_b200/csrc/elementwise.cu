@@ -434,6 +434,75 @@ __global__ void __launch_bounds__(256) subsample_first_kernel(const TIn* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ conv 0 as a GEMM
+// First strided convolution (1 -> C channels, 3x3, stride 2, pad 1; subsampling.py:99-105) on the tensor cores: this
+// kernel gathers the 3x3 patch of every output position into one row of a bf16 matrix A0 whose row order IS the
+// parity-split channels-last layout of y1 ([B][plane][Th][Fh]), and gemm_tc_kernel<EPI_RELU> multiplies it with the
+// (C x 24) weight, writing y1 with its ordinary 2-D TMA stores.  Row = [x_hi (9) | x_lo (9) | 1 | 1 | 0 0 0 0]: the
+// fp32 feature is split into two bf16 values (hi + lo carries 16 mantissa bits) and the bias rides on the two
+// constant columns the same way, so only the nine weights are rounded to bf16.  Rows of positions outside (T1, F1)
+// -- the padding of the planes -- are all zero, which makes relu(0) = 0 exactly what the second conv must see.
+constexpr int kA0Cols = 24;
+template <typename TIn>
+__global__ void __launch_bounds__(256) conv0_im2col_kernel(const TIn* __restrict__ feats, bf16* __restrict__ a0, int F,
+                                                           int T, int T1, int F1, int Th, int Fh) {
+  extern __shared__ float patch[];  // [F + 2][2*kS1T + 2]: frames 2*t1_0 - 1 .. 2*(t1_0 + kS1T - 1) + 1
+  const int pw = 2 * kS1T + 2;
+  const int tblocks = (2 * Th + kS1T - 1) / kS1T;
+  const int b = blockIdx.x / tblocks;
+  const int t1_0 = (blockIdx.x % tblocks) * kS1T;
+  const TIn* xb = feats + static_cast<long long>(b) * F * T;
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = threadIdx.x; i < (F + 2) * (2 * kS1T + 1); i += 256) {
+    const int fr = i / (2 * kS1T + 1), tc = i % (2 * kS1T + 1);
+    const int f = fr - 1, t = 2 * t1_0 - 1 + tc;
+    float v = 0.f;
+    if (f >= 0 && f < F && t >= 0 && t < T) v = static_cast<float>(xb[static_cast<long long>(f) * T + t]);
+    patch[fr * pw + tc] = v;
+  }
+  __syncthreads();
+  const int positions = kS1T * 2 * Fh;
+  for (int pos = threadIdx.x; pos < positions; pos += 256) {
+    // consecutive threads -> consecutive rows of one plane (same f1 parity), then the other parity, then the next t1
+    const int fh = pos % Fh;
+    const int pf = (pos / Fh) & 1;
+    const int tt = pos / (2 * Fh);
+    const int f1 = 2 * fh + pf;
+    const int t1 = t1_0 + tt;
+    if (t1 >= 2 * Th) break;
+    uint32_t w[kA0Cols / 2];
+#pragma unroll
+    for (int j = 0; j < kA0Cols / 2; ++j) w[j] = 0u;
+    if (t1 < T1 && f1 < F1) {
+      unsigned short hi[9], lo[9];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float v = patch[(2 * f1 + kw) * pw + (2 * tt + kh)];
+          const bf16 h = __float2bfloat16_rn(v);
+          const bf16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+          hi[kh * 3 + kw] = __bfloat16_as_ushort(h);
+          lo[kh * 3 + kw] = __bfloat16_as_ushort(l);
+        }
+      unsigned short row[kA0Cols];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) row[q] = hi[q], row[9 + q] = lo[q];
+      row[18] = row[19] = 0x3F80;  // bf16 1.0: the two halves of the bias
+      row[20] = row[21] = row[22] = row[23] = 0;
+#pragma unroll
+      for (int j = 0; j < kA0Cols / 2; ++j) w[j] = static_cast<uint32_t>(row[2 * j]) | (static_cast<uint32_t>(row[2 * j + 1]) << 16);
+    }
+    const int plane = (t1 & 1) * 2 + pf;
+    const long long r = ((static_cast<long long>(b) * 4 + plane) * Th + (t1 >> 1)) * Fh + fh;
+    uint4* dst = reinterpret_cast<uint4*>(a0 + r * kA0Cols);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ im2col (validation)
 __global__ void im2col_kernel(const float* __restrict__ y, float* __restrict__ cols, int B, int C, int Th, int Fh,
                               int To, int Fo) {
@@ -560,6 +629,20 @@ int launch_subsample_first(const void* feats, bool feats_bf16, const float* w9, 
       CFB_S1(float, float);
   }
 #undef CFB_S1
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_conv0_im2col(const void* feats, bool feats_bf16, void* a0, int B, int F, int T, int T1, int F1, int Th, int Fh,
+                        cudaStream_t st) {
+  if (B <= 0) return 0;
+  const int tblocks = (2 * Th + kS1T - 1) / kS1T;
+  const size_t smem = static_cast<size_t>(F + 2) * (2 * kS1T + 2) * sizeof(float);
+  if (feats_bf16)
+    launch_pdl(conv0_im2col_kernel<bf16>, dim3(B * tblocks), dim3(256), smem, st, reinterpret_cast<const bf16*>(feats),
+               reinterpret_cast<bf16*>(a0), F, T, T1, F1, Th, Fh);
+  else
+    launch_pdl(conv0_im2col_kernel<float>, dim3(B * tblocks), dim3(256), smem, st, reinterpret_cast<const float*>(feats),
+               reinterpret_cast<bf16*>(a0), F, T, T1, F1, Th, Fh);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -60,7 +60,7 @@ struct cfb_handle {
   // device arena
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
-  Slot sub_w1, sub_b1, sub_w2, sub_b2, sub_w3, sub_b3, w_pos, div_term, w_oproj, b_oproj;
+  Slot sub_w1, sub_b1, sub_w1g, sub_w2, sub_b2, sub_w3, sub_b3, w_pos, div_term, w_oproj, b_oproj;
   std::vector<LayerW> layers;
   int launches = 0;
   // two-stream micro-batching (see cfb_forward): the second half of a batch runs on an auxiliary stream
@@ -97,7 +97,7 @@ int conv_out(int n) { return (n - 1) / 2 + 1; }  // k=3, s=2, p=1 (n >= 1)
 
 struct Plan {
   int B, T, T1, T2, Th, N, P;  // P = 2*T2-1
-  size_t y1, y2, x, a, hbuf, qkv, ctx, g, c, pe, pos, raw, cols, total;
+  size_t y1, y2, x, a, hbuf, qkv, ctx, g, c, pe, pos, a0, raw, cols, total;
 };
 
 Plan make_plan(const cfb_handle* h, int B, int T) {
@@ -128,6 +128,7 @@ Plan make_plan(const cfb_handle* h, int B, int T) {
   p.c = take(N * h->d * e);
   p.pe = take(static_cast<size_t>(p.P) * h->d * e);
   p.pos = take(static_cast<size_t>(p.P) * h->L * h->Dp * e);
+  p.a0 = h->validate ? 0 : take(static_cast<size_t>(B) * 4 * p.Th * h->Fh * kConv0Cols * 2);  // first conv's GEMM operand
   if (h->validate) {
     size_t raw = N * h->dff;
     raw = std::max(raw, N * 3 * h->Dp);
@@ -352,6 +353,17 @@ int cfb_finalize_weights(cfb_handle* h) {
   if (!missing.empty()) return fail(h, CFB_ERR_MISSING_WEIGHT, "cfb_finalize_weights: " + missing);
   h->sub_w1 = ab.put_f32(c0w->data);
   h->sub_b1 = ab.put_f32(c0b->data);
+  {
+    // (C x 24) bf16 weight of the GEMM form of the first conv: [w (9) | w (9) | bias_hi | bias_lo | 0 x 4]
+    std::vector<float> w(static_cast<size_t>(C) * kConv0Cols, 0.f);
+    for (int n = 0; n < C; ++n) {
+      for (int q = 0; q < 9; ++q) w[static_cast<size_t>(n) * kConv0Cols + q] = w[static_cast<size_t>(n) * kConv0Cols + 9 + q] = c0w->data[n * 9 + q];
+      const float bh = __bfloat162float(__float2bfloat16_rn(c0b->data[n]));
+      w[static_cast<size_t>(n) * kConv0Cols + 18] = bh;
+      w[static_cast<size_t>(n) * kConv0Cols + 19] = c0b->data[n] - bh;
+    }
+    h->sub_w1g = ab.put_mat(w, false);
+  }
   {
     std::vector<float> w(static_cast<size_t>(C) * 9 * C);
     for (int n = 0; n < C; ++n)
@@ -732,10 +744,23 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
   CFB_TRY(launch_lengths(reinterpret_cast<const long long*>(lengths), encoded_len, B, T, 2, st), "lengths");
   ++launches;
   // ---- subsampling: conv 1->C, conv C->C, linear (subsampling.py:172-175)
+  const char* c0_var = getenv("CFB_CONV0_GEMM");  // 0 = CUDA-core kernel; default: patch gather + tcgen05 GEMM
+  if (!v && !(c0_var != nullptr && atoi(c0_var) == 0)) {
+    CFB_TRY(launch_conv0_im2col(feats, feats_dtype == CFB_BF16, ws + pl.a0, B, h->F0, T, pl.T1, h->F1, pl.Th, h->Fh, st),
+            "subsample conv 0 (gather)");
+    ++launches;
+    EpiParams ep;
+    ep.out = ws + pl.y1;
+    ep.ldo = C;
+    CFB_TRY(gemm(ws + pl.a0, kConv0Cols, h->sub_w1g, kConv0Cols, B * 4 * pl.Th * h->Fh, C, kConv0Cols, EPI_RELU, true, ep,
+                 "subsample conv 0"),
+            "subsample conv 0");
+  } else {
   CFB_TRY(launch_subsample_first(feats, feats_dtype == CFB_BF16, h->at<float>(h->sub_w1), h->at<float>(h->sub_b1),
                                  ws + pl.y1, abf, B, h->F0, T, C, pl.T1, h->F1, pl.Th, h->Fh, st),
           "subsample conv 0");
   ++launches;
+  }
   if (v) {
     CFB_TRY(launch_im2col(reinterpret_cast<const float*>(ws + pl.y1), reinterpret_cast<float*>(ws + pl.cols), B, C,
                           pl.Th, h->Fh, T2, F2, st),
@@ -1105,7 +1130,7 @@ int cfb_op_gemm_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const
   return rc == 0 ? CFB_OK : op_fail(rc, err);
 }
 
-int cfb_op_gemm_lna(int epilogue, const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* x_out,
+static int op_gemm_lnt_impl(int epilogue, const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* x_out,
                     const float* gamma2, const float* beta2, const void* W, int64_t ldw, const float* bias,
                     const float* bias2, int M, int N, int d, void* out, int64_t ldo, const int32_t* lens,
                     int frames_per_seq, int qkv_dp, cfb_stream stream) {
@@ -1131,8 +1156,16 @@ int cfb_op_gemm_lna(int epilogue, const float* x, int64_t ldx, const float* gamm
   g.ep.frames_per_seq = frames_per_seq > 0 ? frames_per_seq : 1;
   g.ep.qkv_dp = qkv_dp;
   std::string err;
-  int rc = launch_gemm_lna(g, reinterpret_cast<cudaStream_t>(stream), &err);
+  int rc = launch_gemm_lnt(g, reinterpret_cast<cudaStream_t>(stream), &err);
   return rc == 0 ? CFB_OK : op_fail(rc, err);
+}
+
+int cfb_op_gemm_lnt(int epilogue, const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* x_out,
+                    const float* gamma2, const float* beta2, const void* W, int64_t ldw, const float* bias,
+                    const float* bias2, int M, int N, int d, void* out, int64_t ldo, const int32_t* lens,
+                    int frames_per_seq, int qkv_dp, cfb_stream stream) {
+  return op_gemm_lnt_impl(epilogue, x, ldx, gamma1, beta1, x_out, gamma2, beta2, W, ldw, bias, bias2, M, N, d, out, ldo,
+                          lens, frames_per_seq, qkv_dp, stream);
 }
 
 int cfb_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows, int d,

@@ -400,6 +400,14 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
     if (err) *err = "gemm_tc: K and leading dimensions must be multiples of 8 (16-byte TMA strides)";
     return -1;
   }
+  {
+    // CTA pairs (gemm_tc2.cu): CFB_GEMM_2CTA=0 never, =1 whenever the shape allows, unset = the measured default
+    const char* v2 = getenv("CFB_GEMM_2CTA");
+    const int mode = v2 ? atoi(v2) : -1;
+    // measured (r02j/l, M = 16000): N 2048 K 512 plain 35.0 -> 31.6 us, qkv 33.1 -> 29.6, linear1+swish 36.2 -> 35.7
+    // (its MUFU-bound epilogue takes over), pw1+glu 21.3 -> 22.1, K = 2048 neutral
+    if (mode != 0 && gemm_tc2_supported(g) && (mode == 1 || (g.K <= 1024 && g.N >= 1536))) return launch_gemm_tc2(g, st, err);
+  }
   // tile width: 256 for wide outputs when it does not hurt the wave count, else 128
   const int m_tiles = (g.M + kBlockM - 1) / kBlockM;
   // 256-wide tiles halve the re-reads of A (the kernel is bound by L2->SM bandwidth, not by the tensor pipe)

@@ -155,11 +155,12 @@ CFB_API int cfb_op_gemm_ln(const void* A, int64_t lda, const void* W, int64_t ld
                    const float* beta2, int M, int N, int K, float* out_f32, int64_t ld_out_f32, void* out_bf16,
                    int64_t ld_out_bf16, const int32_t* lens, int frames_per_seq, cfb_stream stream);
 
-/* GEMM with a LayerNorm prologue (tcgen05 path only, K = d <= 512, bf16 output):
+/* GEMM with a LayerNorm prologue (tcgen05 path only, K = d <= 512 and a multiple of 64, bf16 output):
  *   y = LayerNorm(x; gamma1, beta1) -> x_out (fp32, may alias x)   if gamma1 != NULL (norm_out), else y = x
  *   out = epilogue( bf16(LayerNorm(y; gamma2, beta2)) W^T + bias )  epilogue in {LINEAR, SWISH, QKV, GLU}
- * The normalised rows live only in shared memory (the A operand of the CTA's whole row block). */
-CFB_API int cfb_op_gemm_lna(int epilogue, const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* x_out,
+ * The normalised rows live in TENSOR memory (the UMMA A operand is read from TMEM), so only the weight streams through
+ * shared memory (gemm_lnt.cu).  Experimental: bit-identical to cfb_op_layernorm + cfb_op_gemm but slower. */
+CFB_API int cfb_op_gemm_lnt(int epilogue, const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* x_out,
                     const float* gamma2, const float* beta2, const void* W, int64_t ldw, const float* bias,
                     const float* bias2, int M, int N, int d, void* out, int64_t ldo, const int32_t* lens,
                     int frames_per_seq, int qkv_dp, cfb_stream stream);

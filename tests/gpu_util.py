@@ -47,13 +47,15 @@ def op_gemm_ln(A, W, bias, alpha=1.0, resid=None, ln1=None, ln2=None, out_f32=No
     torch.cuda.synchronize()
 
 
-def op_gemm_lna(epi, x, W, ln2, out, bias=None, bias2=None, ln1=None, x_out=None, lens=None, frames_per_seq=1, qkv_dp=0):
-    """GEMM with LayerNorm prologue (cfb_op_gemm_lna).  x (M,d) fp32; ln1 / ln2: (gamma, beta)."""
+def op_gemm_lna(epi, x, W, ln2, out, bias=None, bias2=None, ln1=None, x_out=None, lens=None, frames_per_seq=1, qkv_dp=0,
+                tmem=True):
+    """GEMM with LayerNorm prologue (cfb_op_gemm_lnt).  x (M,d) fp32; ln1 / ln2: (gamma, beta)."""
     lib = _lib.load_library()
     M, d = x.shape
     N = W.shape[0]
     g1, b1 = ln1 if ln1 is not None else (None, None)
-    rc = lib.cfb_op_gemm_lna(epi, ptr(x), x.stride(0), ptr(g1), ptr(b1), ptr(x_out), ptr(ln2[0]), ptr(ln2[1]), ptr(W),
+    fn = lib.cfb_op_gemm_lnt
+    rc = fn(epi, ptr(x), x.stride(0), ptr(g1), ptr(b1), ptr(x_out), ptr(ln2[0]), ptr(ln2[1]), ptr(W),
                              W.stride(0), ptr(bias), ptr(bias2), M, N, d, ptr(out), out.stride(0), ptr(lens),
                              frames_per_seq, qkv_dp, stream())
     assert rc == 0, _lib.last_error(None)
