@@ -210,6 +210,29 @@ def algorithmic_costs(kw, batches):
     return fl, by
 
 
+def gemm_algorithmic_bytes(kw, batches):
+    """Per-step compulsory bytes of the GEMM family (operands read once, result written once; the fp32 residual
+    stream is read and written by the reduce-add epilogues), keyed like algorithmic_costs."""
+    d, L = kw["d_model"], kw["n_layers"]
+    ff, f2 = 4 * d, 20
+    by = {}
+    for lens in batches:
+        t2s = [_out_frames(t)[1] for t in lens]
+        n, p = sum(t2s), 2 * max(t2s) - 1
+        def add(key, m, nn, k, out_b, launches, resid=False):
+            by[key] = by.get(key, 0) + launches * (m * k * 2 + nn * k * 2 + m * nn * out_b * (2 if resid else 1))
+        add("pre_encode.out", n, d, f2 * d, 4, 1)
+        add("linear_pos", p, L * d, d, 2, 1)
+        add("qkv projection", n, 3 * d, d, 2, L)
+        by["qkv projection"] += L * n * d * 2  # the q + v copy
+        add("linear_out", n, d, d, 4, L, resid=True)
+        add("pointwise_conv1+glu", n, 2 * d, d, 1, L)  # GLU halves the output: d bf16 columns = 2d * 1 byte
+        add("pointwise_conv2", n, d, d, 4, L, resid=True)
+        add("linear1+swish", n, ff, d, 2, 2 * L)
+        add("linear2", n, d, ff, 4, 2 * L, resid=True)
+    return by
+
+
 GEMM_LABELS = ["pre_encode.out", "linear_pos", "qkv projection", "linear_out", "pointwise_conv1+glu", "pointwise_conv2",
                "linear1+swish", "linear2"]  # the fused depthwise+pointwise_conv2 kernel is not gemm_tc_kernel: reported apart
 
@@ -439,13 +462,26 @@ def run_b200(args):
                 ach = by[label] / (per_fwd_ms / 1e3) / 1e9
                 ent.update(bound="hbm", achieved=round(ach, 1), unit="GB/s", frac=round(ach / pk["gbs"], 4))
             kernels[label] = ent
+        gemm_bytes = gemm_algorithmic_bytes(kw, [ln.tolist() for _, ln in host_batches])
         gemm_ms = sum(rep[l][1] for l in GEMM_LABELS if l in rep) / prof_steps
         gemm_fl = sum(fl[l] for l in GEMM_LABELS if l in rep)
         gemm_launches = sum(rep[l][0] for l in GEMM_LABELS if l in rep) // prof_steps
         ach = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-        roofline = {"kernel": "gemm_tc_kernel (tcgen05 GEMM family: " + ", ".join(GEMM_LABELS) + ")",
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch of the same kernels from the committed ncu --set full capture (tools/ncu_summary.py)
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic_gemm.json")) as f:
+                tj = json.load(f)
+            if args.workload == "cfg2":
+                traffic, traffic_src = round(tj["traffic_bytes_per_launch"]), f"profiles/{tj['report']} ({tj['how']})"
+        except (OSError, KeyError, ValueError):
+            pass
+        roofline = {"kernel": "gemm_tc_kernel / gemm_tc2_kernel (tcgen05 GEMM family, single CTA and CTA pair: "
+                              + ", ".join(GEMM_LABELS) + ")",
                     "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tflops"], "unit": "TFLOP/s",
-                    "frac": round(ach / pk["tflops"], 4), "traffic": None, "peak_source": pk["source"],
+                    "frac": round(ach / pk["tflops"], 4), "traffic": traffic, "traffic_unit": "bytes per launch (DRAM read + write)",
+                    "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": round(sum(gemm_bytes.get(l, 0) for l in GEMM_LABELS if l in rep) / max(gemm_launches, 1)),
+                    "peak_source": pk["source"],
                     "launches_per_step": gemm_launches, "avg_launch_ms": round(gemm_ms / max(gemm_launches, 1), 5),
                     "share_of_step": round(gemm_ms / sum(v[1] for v in rep.values()) * prof_steps, 4),
                     "how": f"CUDA events around every launch, {prof_steps} extra steps after the timed region"}

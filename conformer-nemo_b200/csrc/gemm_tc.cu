@@ -315,7 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_arrive(&acc_empty[buf]);
       if (trc) p.trace[it * 4 + 2] = clock64();
     }
-    if (lane == 0) ptx::bulk_wait<0>();  // all output writes complete before the CTA retires
+    if (lane == 0) ptx::bulk_wait_read<0>();  // staging boxes outlive their reads; the global side completes with the grid
   }
 
   ptx::tc_fence_before();

@@ -13,7 +13,10 @@ CASES = [("linear1+swish", "SWISH", 2048, 512, "bf16"), ("linear2", "RESID", 512
          ("qkv", "QKV", 1536, 512, "bf16"), ("linear_out", "RESID", 512, 512, "f32"),
          ("pw1+glu", "GLU", 1024, 512, "bf16"), ("plain bf16 N512", "LINEAR", 512, 512, "bf16"),
          ("plain bf16 N2048", "LINEAR", 2048, 512, "bf16"), ("plain f32 N512 K2048", "LINEAR", 512, 2048, "f32")]
+CASES.append(("conv0 as GEMM (M=1.28M)", "RELU", 512, 24, "bf16"))
+M0 = M
 for name, epi, N, K, od in CASES:
+    M = 1280000 if K == 24 else M0
     A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
     W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
     bias = torch.randn(N, device="cuda")
@@ -49,6 +52,7 @@ for name, epi, N, K, od in CASES:
             if v[0] > 0:
                 print("   tile 2 box", bx, "(start | drained | ld+math+sts | fence | store issued):", [x - v[0] for x in v])
 
+M = M0
 # ---- LayerNorm-prologue GEMM (gemm_lnt.cu) against LayerNorm kernel + GEMM
 from gpu_util import op_layernorm  # noqa: E402
 d = 512

@@ -56,9 +56,32 @@ def launches(path):
     print(f"total | {sum(v[0] for v in agg.values())} | {tot:.0f} | 100 %")
 
 
+def traffic(path, regex, out_json):
+    """Average DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels whose name matches
+    `regex` in a --set full report -> a small JSON that bench.py copies into roofline.traffic."""
+    import json
+    import re
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for r in rows[2:]:
+        if re.search(regex, r[kn]):
+            tot += float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]]
+            n += 1
+    json.dump({"kernel_regex": regex, "launches": n, "traffic_bytes_per_launch": tot / max(n, 1), "report": path.split("/")[-1],
+               "how": "ncu --set full --clock-control none (cold L2 per replayed launch), dram__bytes_read.sum + dram__bytes_write.sum averaged over the captured launches"},
+              open(out_json, "w"), indent=1)
+    print(f"{n} launches, {tot / max(n, 1) / 1e6:.1f} MB per launch -> {out_json}")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "--launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "--traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
         for p in sys.argv[2:]:
             full(sys.argv[1], p)
