@@ -144,6 +144,8 @@ long long* g_gemm_trace_view();
 int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err);
 int launch_gemm_simt(const GemmDesc& g, float* scratch, cudaStream_t st, std::string* err);
 int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err);
+// persistent form (one CTA per SM walks over the (query tile, head, sequence) items; attention_tcp.cu)
+int launch_attn_tcp(const AttnDesc& a, cudaStream_t st, std::string* err);
 int launch_attn_simt(const AttnDesc& a, cudaStream_t st, std::string* err);
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int rows, int d,

@@ -132,3 +132,41 @@ def test_tc_matches_simt_on_bf16_inputs():
     op_gemm(False, _lib.EPI_LINEAR, Ab.float(), Wb.float(), out=o_ref)
     st = err_stats(o_tc, o_ref)
     assert st["nan"] == 0 and st["max_abs"] < 1e-4, st
+
+
+@pytest.mark.parametrize("epi", ["LINEAR", "SWISH", "RESID", "QKV", "GLU"])
+@pytest.mark.parametrize("M,N,K", [(129, 256, 64), (300, 512, 176), (1000, 1536, 512), (16000, 2048, 512), (257, 768, 2048)])
+def test_cta_pair_kernel_is_bit_identical_to_the_single_cta_kernel(epi, M, N, K, monkeypatch):
+    """gemm_tc2.cu (cta_group::2, 256 x 256 tiles per CTA pair) against gemm_tc.cu on the same operands: same
+    k-block order and the same epilogue arithmetic -> identical bits, including M tails where the second CTA of the
+    last pair owns no valid row.  CFB_GEMM_2CTA forces either kernel (the default picks by shape)."""
+    A, W = _mk(M, N, K, seed=5)
+    A, W = A.bfloat16(), W.bfloat16()
+    bias = torch.randn(N, device="cuda") * 0.3
+    frames = 50
+    kw = {}
+    if epi == "QKV":
+        if N % 3:
+            pytest.skip("QKV needs N = 3 * Dp")
+        dp = N // 3
+        kw = dict(bias2=torch.randn(dp, device="cuda") * 0.3, qkv_dp=dp)
+        ncols, dt = N + dp, torch.bfloat16
+    elif epi == "GLU":
+        kw = dict(lens=torch.randint(0, frames + 1, ((M + frames - 1) // frames,), device="cuda", dtype=torch.int32),
+                  frames_per_seq=frames)
+        ncols, dt = N // 2, torch.bfloat16
+    elif epi == "RESID":
+        kw = dict(alpha=0.5)
+        ncols, dt = N, torch.float32
+    else:
+        ncols, dt = N, torch.bfloat16
+    outs = []
+    for mode in ("0", "1", "1"):  # the pair kernel twice: run-to-run repeatability
+        monkeypatch.setenv("CFB_GEMM_2CTA", mode)
+        gen = torch.Generator(device="cuda").manual_seed(9)
+        out = torch.randn(M, ncols, device="cuda", generator=gen).to(dt) if epi == "RESID" else torch.full(
+            (M, ncols), float("nan"), device="cuda", dtype=dt)
+        op_gemm(True, getattr(_lib, "EPI_" + epi), A, W, bias=bias, out=out, **kw)
+        outs.append(out)
+    assert int(torch.isnan(outs[0].float()).sum()) == 0
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]), err_stats(outs[1].float(), outs[0].float())
