@@ -16,11 +16,14 @@ LPS=$(python -c "import json,sys; print([json.loads(l)['launches_per_step'] for 
 echo "launches per step: $LPS"
 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3*LPS)) -c $LPS --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 300 -c 24 -o gpurun_out/${TAG}_gemm $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
+# the --set full captures run the forward as ONE batch (CFB_MICROBATCH=0), like bench.py's per-kernel timing pass, so
+# per-launch figures (DRAM bytes, durations) refer to the same launches as roofline.achieved
+export CFB_MICROBATCH=0
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 150 -c 24 -o gpurun_out/${TAG}_gemm $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "ncu gemm rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:rel_attn_tc -s 20 -c 2 -o gpurun_out/${TAG}_attn $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rel_attn_tc -s 10 -c 2 -o gpurun_out/${TAG}_attn $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
 echo "ncu attn rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"dw_pw|layernorm|conv0_im2col" -s 30 -c 10 -o gpurun_out/${TAG}_mem $CMD > gpurun_out/${TAG}_ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"dw_pw|layernorm|conv0_im2col" -s 15 -c 10 -o gpurun_out/${TAG}_mem $CMD > gpurun_out/${TAG}_ncu4.log 2>&1
 echo "ncu mem rc=$?"
 ls -la gpurun_out | tail -12
 fi
