@@ -325,7 +325,7 @@ def run_b200(args):
         step()
         torch.cuda.synchronize()
         if rank == 0:
-            print(json.dumps({"ncu_helper": True, "launches_per_step": launches_per_step}))
+            emit({"ncu_helper": True, "launches_per_step": launches_per_step})
         return
     # a fresh box needs a moment of sustained load before clocks / power state settle: keep warming for ~1 s
     torch.cuda.synchronize()
@@ -510,7 +510,7 @@ def run_b200(args):
         "launch_mode": "eager" if args.no_graphs else "cuda graph replay", "eager_ms_per_step": eager_ms,
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def time_oracle(kw, sd, sample_b, t, warmup, steps):
@@ -558,10 +558,27 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The contract line goes to the process's ORIGINAL stdout; everything else (NCCL's version banner, library
+    chatter, stray prints) was re-pointed at stderr by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _JSON_OUT
+    # stdout carries exactly one JSON line: keep a private handle to it and send file descriptor 1 to stderr, so that
+    # C-level writers (NCCL prints its banner with printf at NCCL_DEBUG=VERSION / WARN) cannot get in front of it
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

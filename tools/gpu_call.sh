@@ -1,7 +1,6 @@
-timeout 900 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider 2>&1 | grep -v "^E  " | tail -12 | tee gpurun_out/r02u_pytest_gpu.log
-python bench.py --steps 20 --warmup 3 > gpurun_out/r02u_bench.json 2> gpurun_out/r02u_bench.err
-python tools/show_bench.py gpurun_out/r02u_bench.json | head -4
-python bench.py --steps 20 --warmup 3 --workload cfg4 --no-cpu-baseline > gpurun_out/r02u_bench_cfg4.json 2> gpurun_out/r02u_bench_cfg4.err
-python tools/show_bench.py gpurun_out/r02u_bench_cfg4.json | head -3
-CFB_ATTN_PERSIST=0 python bench.py --steps 20 --warmup 3 --workload cfg4 --no-cpu-baseline > gpurun_out/r02u_bench_cfg4_np.json 2> gpurun_out/r02u_bench_cfg4_np.err
-python tools/show_bench.py gpurun_out/r02u_bench_cfg4_np.json | head -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02w_bench_2gpu.json 2> gpurun_out/r02w_bench_2gpu.err
+echo "rc=$?"; tail -2 gpurun_out/r02w_bench_2gpu.err; python tools/show_bench.py gpurun_out/r02w_bench_2gpu.json 2>/dev/null | head -2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r02w_ref_2gpu.json 2> gpurun_out/r02w_ref_2gpu.err
+echo "rc=$?"; tail -2 gpurun_out/r02w_ref_2gpu.err; cat gpurun_out/r02w_ref_2gpu.json | cut -c1-600
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 2 --steps 10 --warmup 3 --workload cfg3 > gpurun_out/r02w_bench_cfg3_2gpu.json 2> gpurun_out/r02w_bench_cfg3_2gpu.err
+echo "rc=$?"; python tools/show_bench.py gpurun_out/r02w_bench_cfg3_2gpu.json 2>/dev/null | head -2
