@@ -80,3 +80,28 @@ def test_tc_attention_matches_reference(B, T, H, dk, lens):
     assert st["nan"] == 0 and st["rel_l2"] < 1.5e-2 and st["max_abs"] < 6e-2, st
     for b, n in enumerate(lens):
         assert torch.all(got[b, n:] == 0)
+
+
+@pytest.mark.parametrize("B,T,H,seed", [(40, 300, 8, 0), (64, 90, 4, 1), (7, 1000, 8, 2), (300, 40, 2, 3)])
+def test_persistent_attention_is_bit_identical_to_the_per_item_kernel(B, T, H, seed, monkeypatch):
+    """attention_tcp.cu (one CTA per SM walks over the (query tile, head, sequence) items, pipelines and barrier phases
+    continuous across items) against attention_tc.cu (one CTA per item) on ragged batches with far more items than
+    SMs: empty sequences, sequences of one key tile (the second softmax set idles), padded query tiles between active
+    ones.  Same arithmetic: identical bits; and both against the torch restatement of the reference."""
+    dk = 64
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(0, T + 1, (B,), generator=g).tolist()
+    lens[0], lens[1 % B], lens[2 % B], lens[-1] = T, 0, min(T, 64), min(T, 65)
+    qkv, pos, lens_t, want, Dp = make_case(B, T, H, dk, lens, seed + 10, torch.bfloat16)
+    outs = []
+    for mode in ("0", "1", "1"):
+        monkeypatch.setenv("CFB_ATTN_PERSIST", mode)
+        ctx = torch.full((B * T, Dp), float("nan"), device="cuda", dtype=torch.bfloat16)
+        op_attention(True, qkv.bfloat16(), pos.bfloat16()[:, Dp:], ctx, lens_t, B, T, H, dk)
+        outs.append(ctx)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    got = outs[1].float().view(B, T, H, 64)
+    st = err_stats(got[..., :dk], want)
+    assert st["nan"] == 0 and st["rel_l2"] < 1.5e-2 and st["max_abs"] < 6e-2, st
+    for b, n in enumerate(lens):
+        assert torch.all(got[b, n:] == 0)
