@@ -113,3 +113,39 @@ def load_reference_ctc_decoder_class():
         sys.modules["omegaconf"] = om
     mod = importlib.import_module("nemo.collections.asr.modules.conv_asr")
     return mod.ConvASRDecoder
+
+
+def load_reference_filterbank_class():
+    """Returns the reference ``FilterbankFeatures`` class (parts/preprocessing/features.py:196), executed unmodified.
+    features.py imports librosa, torch_stft and two sibling modules (perturb, segment) that need soundfile / sox: inert
+    stand-ins are registered for them.  The only one that contributes arithmetic is ``librosa.filters.mel``, which is
+    served by oracle.frontend_oracle.slaney_mel_filters (see that module's header)."""
+    load_reference_encoder_class()  # registers the stub packages and nemo.utils.logging
+    if "nemo.collections.asr.parts.preprocessing.features" in sys.modules:
+        return sys.modules["nemo.collections.asr.parts.preprocessing.features"].FilterbankFeatures
+    import numpy as np
+
+    from oracle.frontend_oracle import slaney_mel_filters
+
+    _stub_package("nemo.collections.asr.parts.preprocessing",
+                  os.path.join(REFERENCE_ROOT, "nemo/collections/asr/parts/preprocessing"))
+    librosa = types.ModuleType("librosa")
+    librosa.filters = types.ModuleType("librosa.filters")
+    librosa.filters.mel = lambda sr, n_fft, n_mels=128, fmin=0.0, fmax=None, **_k: slaney_mel_filters(sr, n_fft, n_mels, fmin, fmax)
+    librosa.util = types.ModuleType("librosa.util")
+    librosa.util.tiny = lambda x: np.finfo(np.float32).tiny
+    sys.modules.update({"librosa": librosa, "librosa.filters": librosa.filters, "librosa.util": librosa.util})
+    ts = types.ModuleType("torch_stft")
+    ts.STFT = type("STFT", (), {})
+    sys.modules["torch_stft"] = ts
+    for name, attr in (("perturb", "AudioAugmentor"), ("segment", "AudioSegment")):
+        m = types.ModuleType("nemo.collections.asr.parts.preprocessing." + name)
+        setattr(m, attr, type(attr, (), {}))
+        sys.modules[m.__name__] = m
+    utils = sys.modules["nemo.utils"]
+    if not hasattr(utils.logging, "warning"):
+        import logging as _logging
+
+        utils.logging = _logging.getLogger("nemo_stub")
+    mod = importlib.import_module("nemo.collections.asr.parts.preprocessing.features")
+    return mod.FilterbankFeatures
