@@ -177,6 +177,23 @@ bool encode_tmap(CUtensorMap* map, const void* base, bool is_f32, int rank, cons
 bool encode_tmap_ex(CUtensorMap* map, const void* base, bool is_f32, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, std::string* err);
 
+// log-mel front-end (frontend.cu): FilterbankFeatures.forward in eval mode, features.py:358-453
+struct LogMelDesc {
+  const float* audio = nullptr;   // (B, L) fp32 waveforms, zero after each utterance's length
+  const void* lengths = nullptr;  // (B) int64 samples
+  int B = 0, L = 0;
+  const float* window = nullptr;  // (win_length) fp32
+  int win_length = 0, n_fft = 512, hop = 160;
+  const float* fb_km = nullptr;   // (n_fft / 2 + 1, n_mels): the mel filter bank TRANSPOSED (bin-major)
+  int n_mels = 0;
+  float preemph = 0.97f, log_guard = 5.9604644775390625e-08f, std_eps = 1e-5f;
+  float* features = nullptr;      // (B, n_mels, T_out) fp32
+  int T_out = 0;                  // >= 1 + L / hop; frames from seq_len on are written as zeros
+  void* seq_len = nullptr;        // (B) int64
+  int* flag = nullptr;            // set to 1 when some utterance has exactly one frame (the reference raises)
+};
+int launch_logmel(const LogMelDesc& d, cudaStream_t st, std::string* err);
+
 // depth-wise conv (+ folded BatchNorm + Swish) fused into pointwise_conv2 and the residual update (conv_tail.cu):
 //   x[b,t,:] += W2 * swish(bias_dw + sum_k taps[k] * g[b, t + k - 15, :]) + bias2
 // taps32: (32, d) fp32, rows 0..30 = the 31 taps (shorter kernels centred, zero padded), row 31 = the folded bias

@@ -1197,6 +1197,33 @@ int cfb_op_dw_pw2(const void* g, const float* taps32, const void* W, const float
   return rc == 0 ? CFB_OK : op_fail(rc, err);
 }
 
+int cfb_op_logmel(const float* audio, const int64_t* lengths, int B, int L, const float* window, int win_length, int n_fft,
+                  int hop, const float* fb_km, int n_mels, float preemph, float log_guard, float std_eps, float* features,
+                  int T_out, int64_t* seq_len, int32_t* flag, cfb_stream stream) {
+  LogMelDesc d;
+  d.audio = audio;
+  d.lengths = lengths;
+  d.B = B;
+  d.L = L;
+  d.window = window;
+  d.win_length = win_length;
+  d.n_fft = n_fft;
+  d.hop = hop;
+  d.fb_km = fb_km;
+  d.n_mels = n_mels;
+  d.preemph = preemph;
+  d.log_guard = log_guard;
+  d.std_eps = std_eps;
+  d.features = features;
+  d.T_out = T_out;
+  d.seq_len = seq_len;
+  d.flag = flag;
+  if (!audio || !lengths || !window || !fb_km || !features || !seq_len || !flag) return op_fail(-1, "logmel: null pointer");
+  std::string err;
+  int rc = launch_logmel(d, reinterpret_cast<cudaStream_t>(stream), &err);
+  return rc == 0 ? CFB_OK : op_fail(rc, err);
+}
+
 int cfb_op_rel_attention(int use_tc, const void* qkv, const void* pos, int64_t ld_pos, void* ctx, const int32_t* lens,
                          int B, int T, int H, int dk, int dkp, cfb_stream stream) {
   AttnDesc a;

@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests/test_gpu_attention.py tests/test_gpu_gemm.py tests/test_gpu_conv_tail.py -x -q -m gpu --tb=short -p no:cacheprovider 2>&1 | grep -v "^E  " | tail -15 | tee gpurun_out/r02x_tests.log
+timeout 600 python -m pytest tests/test_frontend.py -x -q -m gpu --tb=short -p no:cacheprovider 2>&1 | tail -25 | tee gpurun_out/r02y_test_frontend.log
