@@ -78,7 +78,7 @@ def load_library() -> ctypes.CDLL:
         lib.cfb_op_ctc_head.argtypes = [vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]
         lib.cfb_op_layernorm.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, i32, vp]
         lib.cfb_op_depthwise.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
-        lib.cfb_op_logmel.argtypes = [vp, vp, i32, i32, vp, i32, i32, i32, vp, i32, ctypes.c_float, ctypes.c_float,
+        lib.cfb_op_logmel.argtypes = [vp, vp, i32, i32, vp, i32, i32, i32, vp, vp, i32, ctypes.c_float, ctypes.c_float,
                                       ctypes.c_float, vp, i32, vp, vp, vp]
         lib.cfb_op_dw_pw2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
         lib.cfb_op_rel_attention.argtypes = [i32, vp, vp, i64, vp, vp, i32, i32, i32, i32, i32, vp]

@@ -184,7 +184,8 @@ struct LogMelDesc {
   int B = 0, L = 0;
   const float* window = nullptr;  // (win_length) fp32
   int win_length = 0, n_fft = 512, hop = 160;
-  const float* fb_km = nullptr;   // (n_fft / 2 + 1, n_mels): the mel filter bank TRANSPOSED (bin-major)
+  const float* fb = nullptr;      // (n_mels, n_fft / 2 + 1): the mel filter bank (featurizer.fb)
+  const int* fb_span = nullptr;   // (n_mels, 2) int32: first non-zero FFT bin and bin count of every filter
   int n_mels = 0;
   float preemph = 0.97f, log_guard = 5.9604644775390625e-08f, std_eps = 1e-5f;
   float* features = nullptr;      // (B, n_mels, T_out) fp32

@@ -1198,7 +1198,7 @@ int cfb_op_dw_pw2(const void* g, const float* taps32, const void* W, const float
 }
 
 int cfb_op_logmel(const float* audio, const int64_t* lengths, int B, int L, const float* window, int win_length, int n_fft,
-                  int hop, const float* fb_km, int n_mels, float preemph, float log_guard, float std_eps, float* features,
+                  int hop, const float* fb, const int32_t* fb_span, int n_mels, float preemph, float log_guard, float std_eps, float* features,
                   int T_out, int64_t* seq_len, int32_t* flag, cfb_stream stream) {
   LogMelDesc d;
   d.audio = audio;
@@ -1209,7 +1209,8 @@ int cfb_op_logmel(const float* audio, const int64_t* lengths, int B, int L, cons
   d.win_length = win_length;
   d.n_fft = n_fft;
   d.hop = hop;
-  d.fb_km = fb_km;
+  d.fb = fb;
+  d.fb_span = fb_span;
   d.n_mels = n_mels;
   d.preemph = preemph;
   d.log_guard = log_guard;
@@ -1218,7 +1219,7 @@ int cfb_op_logmel(const float* audio, const int64_t* lengths, int B, int L, cons
   d.T_out = T_out;
   d.seq_len = seq_len;
   d.flag = flag;
-  if (!audio || !lengths || !window || !fb_km || !features || !seq_len || !flag) return op_fail(-1, "logmel: null pointer");
+  if (!audio || !lengths || !window || !fb || !fb_span || !features || !seq_len || !flag) return op_fail(-1, "logmel: null pointer");
   std::string err;
   int rc = launch_logmel(d, reinterpret_cast<cudaStream_t>(stream), &err);
   return rc == 0 ? CFB_OK : op_fail(rc, err);

@@ -3,12 +3,13 @@
 // pre-emphasis, centred STFT with reflect padding (n_fft = 512), |.|^2, mel projection, log(x + guard), per-feature
 // mean / std normalisation over the valid frames, zero padding of the rest.
 //
-//   logmel_frames_kernel     one warp per frame: the 512 windowed, pre-emphasised samples go bit-reversed into a
-//                            private shared-memory buffer, nine radix-2 stages (8 butterflies per lane, twiddles from
-//                            a 256-entry table in shared memory), power spectrum in place, then every lane owns
-//                            mel bins lane, lane + 32, lane + 64 and walks the 257 FFT bins (filter bank transposed to
-//                            (bin, mel) so a warp reads 128 contiguous bytes per bin).  A CTA's 16 frames are staged as
-//                            a (mel, frame) tile and written as 64-byte row segments.
+//   logmel_frames_kernel     one warp per frame: the 512 windowed, pre-emphasised real samples are packed as 256 complex
+//                            values (bit-reversed) in a private shared-memory buffer, eight radix-2 stages (4
+//                            butterflies per lane, twiddles from a 256-entry table in shared memory), one untangling
+//                            pass to the 257 bins of the real transform and their power, then every lane owns mel bins
+//                            lane, lane + 32, lane + 64 and walks only the FFT bins its triangular filter covers
+//                            (spans found once on the host).  A CTA's 16 frames are staged as a (mel, frame) tile and
+//                            written as 64-byte row segments.
 //   logmel_normalize_kernel  one warp per (utterance, mel bin) row: mean, unbiased std + 1e-5 over the valid frames
 //                            (two passes over a row that the first kernel just left in L2), normalised in place,
 //                            zeros from seq_len on; also writes seq_len = floor(len / hop) + 1 computed in float32
@@ -29,87 +30,100 @@ constexpr int kFramesPerCta = 16;
 constexpr int kWarps = 8;
 constexpr int kMaxMels = 96;  // three mel bins per lane
 
-__device__ __forceinline__ int bitrev9(int v) { return static_cast<int>(__brev(static_cast<unsigned>(v)) >> 23); }
+__device__ __forceinline__ int bitrev8(int v) { return static_cast<int>(__brev(static_cast<unsigned>(v)) >> 24); }
 
 __global__ void __launch_bounds__(32 * kWarps)
 logmel_frames_kernel(const float* __restrict__ audio, int L, const float* __restrict__ window, int win_length, int hop,
-                     const float* __restrict__ fb_km, int n_mels, float preemph, float log_guard,
-                     float* __restrict__ feat, int T, int T_out) {
+                     const float* __restrict__ fb, const int* __restrict__ fb_span, int n_mels, float preemph,
+                     float log_guard, float* __restrict__ feat, int T, int T_out) {
+  // per warp: z[256] (the packed half-size FFT) followed by the 257 power values (the second half of the buffer)
   __shared__ float2 buf[kWarps][kNfft];
-  __shared__ float2 tw[kNfft / 2];
+  __shared__ float2 tw[kNfft / 2];  // W_512^k, k < 256
   __shared__ float tile[kMaxMels][kFramesPerCta + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kFramesPerCta;
   for (int k = threadIdx.x; k < kNfft / 2; k += blockDim.x) {
-    float s, c;
-    sincospif(-2.0f * static_cast<float>(k) / kNfft, &s, &c);
-    tw[k] = make_float2(c, s);
+    float sn, cs;
+    sincospif(-2.0f * static_cast<float>(k) / kNfft, &sn, &cs);
+    tw[k] = make_float2(cs, sn);
+  }
+  // this lane's mel bins (lane, lane + 32, lane + 64): first FFT bin and number of bins of each triangular filter
+  int m_start[3], m_len[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int m = lane + 32 * j;
+    m_start[j] = m < n_mels ? __ldg(fb_span + 2 * m) : 0;
+    m_len[j] = m < n_mels ? __ldg(fb_span + 2 * m + 1) : 0;
   }
   pdl_launch_dependents();
   pdl_wait();
   __syncthreads();
   const float* x = audio + static_cast<long long>(b) * L;
   const int w_off = (kNfft - win_length) / 2;  // torch.stft centres a short window inside n_fft
-  float2* my = buf[warp];
+  float2* z = buf[warp];
+  float* pwr = reinterpret_cast<float*>(buf[warp] + kNfft / 2);
+  // windowed sample n of frame t of the pre-emphasised, reflect-padded signal (features.py:371-376; center = True pads
+  // n_fft / 2 samples on both sides of the WHOLE row)
+  auto sample = [&](int t, int n) -> float {
+    const int wn = n - w_off;
+    if (wn < 0 || wn >= win_length) return 0.f;
+    int s = t * hop - kNfft / 2 + n;
+    if (s < 0) s = -s;
+    if (s >= L) s = 2 * (L - 1) - s;
+    s = min(max(s, 0), L - 1);
+    const float cur = __ldg(x + s);
+    const float y = s > 0 ? cur - preemph * __ldg(x + s - 1) : cur;
+    return y * __ldg(window + wn);
+  };
   for (int f = warp; f < kFramesPerCta; f += kWarps) {
     const int t = t0 + f;
     if (t >= T) break;  // warp-uniform
-    // ---- windowed frame of the pre-emphasised, reflect-padded signal (features.py:371-376; center=True pads
-    // n_fft / 2 samples on both sides of the WHOLE row)
-    for (int n = lane; n < kNfft; n += 32) {
-      float v = 0.f;
-      const int wn = n - w_off;
-      if (wn >= 0 && wn < win_length) {
-        int s = t * hop - kNfft / 2 + n;
-        if (s < 0) s = -s;
-        if (s >= L) s = 2 * (L - 1) - s;
-        s = min(max(s, 0), L - 1);
-        const float cur = __ldg(x + s);
-        const float y = s > 0 ? cur - preemph * __ldg(x + s - 1) : cur;
-        v = y * __ldg(window + wn);
-      }
-      my[bitrev9(n)] = make_float2(v, 0.f);
-    }
+    // ---- real 512-point DFT through a 256-point complex FFT of z[n] = x[2n] + i x[2n+1] (bit-reversed store)
+    for (int n = lane; n < kNfft / 2; n += 32) z[bitrev8(n)] = make_float2(sample(t, 2 * n), sample(t, 2 * n + 1));
     __syncwarp();
-    // ---- 512-point radix-2 decimation-in-time FFT
 #pragma unroll 1
-    for (int half = 1; half < kNfft; half <<= 1) {
-      const int tstep = (kNfft / 2) / half;
+    for (int half = 1; half < kNfft / 2; half <<= 1) {
+      const int tstep = (kNfft / 2) / half;  // W_256^j = W_512^(2j): index j * 256 / half into the 512-table
 #pragma unroll
-      for (int q = lane; q < kNfft / 2; q += 32) {
+      for (int q = lane; q < kNfft / 4; q += 32) {
         const int j = q & (half - 1);
         const int i = ((q - j) << 1) + j;
         const float2 w = tw[j * tstep];
-        const float2 a = my[i], c = my[i + half];
+        const float2 a = z[i], c = z[i + half];
         const float2 wc = make_float2(w.x * c.x - w.y * c.y, w.x * c.y + w.y * c.x);
-        my[i] = make_float2(a.x + wc.x, a.y + wc.y);
-        my[i + half] = make_float2(a.x - wc.x, a.y - wc.y);
+        z[i] = make_float2(a.x + wc.x, a.y + wc.y);
+        z[i + half] = make_float2(a.x - wc.x, a.y - wc.y);
       }
       __syncwarp();
     }
-    // ---- power spectrum: the reference takes sqrt(re^2 + im^2) and squares it again (features.py:385, 393-394)
-    for (int k = lane; k < kBins; k += 32) {
-      const float2 z = my[k];
-      const float mag = sqrtf(z.x * z.x + z.y * z.y);
-      my[k].x = mag * mag;
-    }
-    __syncwarp();
-    // ---- mel projection + log (features.py:397-402)
-    float acc[3] = {0.f, 0.f, 0.f};
-    for (int k = 0; k < kBins; ++k) {
-      const float pwr = my[k].x;
-      const float* row = fb_km + static_cast<long long>(k) * n_mels;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int m = lane + 32 * j;
-        if (m < n_mels) acc[j] = fmaf(__ldg(row + m), pwr, acc[j]);
+    // ---- untangle: X[k] = E[k] + W_512^k O[k], E = (Z[k] + conj Z[256-k]) / 2, O = (Z[k] - conj Z[256-k]) / (2i); the
+    // reference takes sqrt(re^2 + im^2) and squares it again (features.py:385, 393-394)
+    for (int k = lane; k < kNfft / 2; k += 32) {
+      const float2 zk = z[k], zn = z[(kNfft / 2 - k) & (kNfft / 2 - 1)];
+      const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+      const float2 w = tw[k];
+      const float re = e.x + (w.x * o.x - w.y * o.y), im = e.y + (w.x * o.y + w.y * o.x);
+      const float mag = sqrtf(re * re + im * im);
+      pwr[k] = mag * mag;
+      if (k == 0) {
+        const float nyq = fabsf(zk.x - zk.y);  // X[256] = E[0] - O[0], purely real
+        pwr[kNfft / 2] = nyq * nyq;
       }
     }
+    __syncwarp();
+    // ---- mel projection over each filter's own bins + log (features.py:397-402)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int m = lane + 32 * j;
-      if (m < n_mels) tile[m][f] = logf(acc[j] + log_guard);
+      if (m < n_mels) {
+        const float* row = fb + static_cast<long long>(m) * kBins + m_start[j];
+        const float* pp = pwr + m_start[j];
+        float acc = 0.f;
+        for (int k = 0; k < m_len[j]; ++k) acc = fmaf(__ldg(row + k), pp[k], acc);
+        tile[m][f] = logf(acc + log_guard);
+      }
     }
     __syncwarp();
   }
@@ -178,7 +192,7 @@ int launch_logmel(const LogMelDesc& d, cudaStream_t st, std::string* err) {
   cudaError_t e = cudaMemsetAsync(d.flag, 0, sizeof(int), st);
   if (e != cudaSuccess) return static_cast<int>(e);
   launch_pdl(logmel_frames_kernel, dim3((T + kFramesPerCta - 1) / kFramesPerCta, d.B), dim3(32 * kWarps), 0, st, d.audio, d.L,
-             d.window, d.win_length, d.hop, d.fb_km, d.n_mels, d.preemph, d.log_guard, d.features, T, d.T_out);
+             d.window, d.win_length, d.hop, d.fb, d.fb_span, d.n_mels, d.preemph, d.log_guard, d.features, T, d.T_out);
   const int rows = d.B * d.n_mels;
   launch_pdl(logmel_normalize_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, d.features,
              reinterpret_cast<const long long*>(d.lengths), rows, d.n_mels, T, d.T_out, d.hop, d.std_eps,

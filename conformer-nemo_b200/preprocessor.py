@@ -157,8 +157,12 @@ class AudioToMelSpectrogramPreprocessor(nn.Module):
         lens = length.to(device=dev, dtype=torch.int64).contiguous()
         B, L = x.shape
         if self._fb_km is None or self._fb_km.device != dev:
-            fb = self.featurizer.fb.to(dev, torch.float32)
-            self._fb_km = fb.reshape(fb.shape[-2], fb.shape[-1]).t().contiguous()
+            fb = self.featurizer.fb.detach().float().cpu().reshape(self.featurizer.fb.shape[-2], self.featurizer.fb.shape[-1])
+            nz = fb != 0  # every filter is summed over its own span of FFT bins only
+            first = torch.where(nz.any(1), nz.float().argmax(1), torch.zeros(fb.shape[0], dtype=torch.long))
+            last = torch.where(nz.any(1), fb.shape[1] - 1 - nz.flip(1).float().argmax(1), -torch.ones(fb.shape[0], dtype=torch.long))
+            self._fb_span = torch.stack([first, last - first + 1], 1).to(torch.int32).contiguous().to(dev)
+            self._fb_km = fb.contiguous().to(dev)
             self._window = self.featurizer.window.to(dev, torch.float32).contiguous()
             self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
         T = 1 + L // self.hop_length
@@ -167,7 +171,7 @@ class AudioToMelSpectrogramPreprocessor(nn.Module):
         seq_len = torch.empty(B, dtype=torch.int64, device=dev)
         vp = ctypes.c_void_p
         rc = lib.cfb_op_logmel(vp(x.data_ptr()), vp(lens.data_ptr()), B, L, vp(self._window.data_ptr()), self.win_length,
-                               self.n_fft, self.hop_length, vp(self._fb_km.data_ptr()), self.nfilt,
+                               self.n_fft, self.hop_length, vp(self._fb_km.data_ptr()), vp(self._fb_span.data_ptr()), self.nfilt,
                                float(self.preemph if self.preemph is not None else 0.0), self.log_zero_guard_value, 1e-5,
                                vp(out.data_ptr()), T_out, vp(seq_len.data_ptr()), vp(self._flag.data_ptr()),
                                vp(torch.cuda.current_stream(dev).cuda_stream))

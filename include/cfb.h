@@ -189,11 +189,12 @@ CFB_API int cfb_op_dw_pw2(const void* g, const float* taps32, const void* W2, co
  * per_feature / log-add / power-2 recipes: pre-emphasis, centred STFT with reflect padding, |.|^2, mel projection,
  * log(x + log_guard), per-(utterance, mel) mean / unbiased-std normalisation over the valid frames, zeros after them.
  * audio (B, L) fp32 (L > n_fft / 2), lengths (B) int64 samples; window (win_length <= n_fft) fp32; n_fft must be 512;
- * fb_km (n_fft / 2 + 1, n_mels <= 96) = the `featurizer.fb` buffer TRANSPOSED; features (B, n_mels, T_out) fp32 with
+ * fb (n_mels <= 96, n_fft / 2 + 1) = the `featurizer.fb` buffer, fb_span (n_mels, 2) int32 = first non-zero bin and
+ * bin count of every filter (the kernel sums each filter over its own bins only); features (B, n_mels, T_out) fp32 with
  * T_out >= 1 + L / hop (the caller rounds up to `pad_to`); seq_len (B) int64 = floor(len / hop) + 1; *flag is set to 1
  * if some utterance has exactly one frame (the reference raises ValueError there).  All pointers are device pointers. */
 CFB_API int cfb_op_logmel(const float* audio, const int64_t* lengths, int B, int L, const float* window, int win_length,
-                  int n_fft, int hop, const float* fb_km, int n_mels, float preemph, float log_guard, float std_eps,
+                  int n_fft, int hop, const float* fb, const int32_t* fb_span, int n_mels, float preemph, float log_guard, float std_eps,
                   float* features, int T_out, int64_t* seq_len, int32_t* flag, cfb_stream stream);
 
 /* Relative-position multi-head attention core (multi_head_attention.py:195-210 + :104-113), everything between the
