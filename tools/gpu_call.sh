@@ -1,2 +1,4 @@
-timeout 600 python -m pytest tests/test_frontend.py -x -q -m gpu --tb=short -p no:cacheprovider 2>&1 | tail -12 | tee gpurun_out/r02y_test_frontend.log
-python tools/bench_frontend.py | tee gpurun_out/r02z_bench_frontend.json
+for wl in cfg3 cfg5 cfg4 tiny; do
+  python bench.py --steps 10 --warmup 3 --workload $wl --no-cpu-baseline > gpurun_out/r03a_bench_$wl.json 2> gpurun_out/r03a_bench_$wl.err
+  echo "$wl rc=$?"; python tools/show_bench.py gpurun_out/r03a_bench_$wl.json 2>/dev/null | head -2 | tail -1
+done

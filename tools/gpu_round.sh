@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box round: parity tests (the driver's own command), bench, and (optionally) the ncu launch list + full
-# captures of the top kernels.  usage: bash tools_gpu_round.sh <tag> [tests|notests] [ncu]
+# captures of the top kernels.  usage: bash tools/gpu_round.sh <tag> [tests|notests] [ncu]
 TAG=${1:-r01}
 mkdir -p gpurun_out
 if [[ "$2" != "notests" ]]; then
