@@ -284,3 +284,98 @@ def test_fused_conv_tail_is_bit_identical_to_the_two_kernel_path(name, monkeypat
     assert torch.equal(y_fused, y_auto)
     st = compare(y_fused.float().cpu(), torch.from_numpy(z["encoded"]), ylen)
     assert st["nan"] == 0 and st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, st
+
+
+def test_full_size_cfg2_properties_and_oracle_sample():
+    """BASELINE.json configs[1] at its full size (Conformer-L: d_model 512, 17 layers, 8 heads; 32 utterances x 2000
+    frames), mixed lengths.  Size-independent properties of the path -- utterances are independent given the padded
+    extent -- are checked BITWISE on the whole batch (product configuration: two-stream micro-batches, fused conv tail,
+    CTA-pair GEMMs, persistent attention), and two utterances are compared with the CPU oracle at full depth."""
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=17, d_model=512, n_heads=8)
+    sd = oc.random_state_dict(cfg, 5)
+    B, T = 32, 2000
+    g = torch.Generator().manual_seed(17)
+    lens = torch.randint(200, T + 1, (B,), generator=g).tolist()
+    lens[0], lens[3] = T, 777
+    x, length = oc.synthetic_batch(B, 80, T, lens, seed=11)
+    enc = build(cfg, sd, "bf16")
+    xd, ld = x.cuda(), length.cuda()
+    y, ylen = enc(audio_signal=xd, length=ld)
+    y = y.clone()
+    ylen = ylen.clone()
+    torch.cuda.synchronize()
+    assert int(torch.isnan(y).sum()) == 0
+    # (1) encoded_len: (L + 1) // 2 twice, int32 (subsampling.py:272-282)
+    want_len = torch.tensor([((n + 1) // 2 + 1) // 2 for n in lens], dtype=torch.int32)
+    assert ylen.dtype == torch.int32 and torch.equal(ylen.cpu(), want_len)
+    # (2) frames past encoded_len are zeros
+    for b in (0, 3, 7):
+        assert torch.all(y[b, :, int(want_len[b]):] == 0)
+    # (3) permuting the utterances permutes the result, bit for bit (rows change micro-batch half and tile position)
+    perm = torch.randperm(B, generator=g)
+    yp, lp = enc(audio_signal=xd[perm.cuda()].contiguous(), length=ld[perm.cuda()].contiguous())
+    assert torch.equal(lp.cpu(), want_len[perm]) and torch.equal(yp, y[perm.cuda()])
+    # (4) an utterance's result does not depend on what the other utterances contain
+    x2 = xd.clone()
+    x2[5] = torch.flip(x2[5], dims=[0])
+    y2, _ = enc(audio_signal=x2, length=ld)
+    keep = [b for b in range(B) if b != 5]
+    assert torch.equal(y2[keep], y[keep]) and not torch.equal(y2[5], y[5])
+    # (5) ... nor on the batch size: the same two utterances alone (same padded extent T)
+    ys, ls = enc(audio_signal=xd[[0, 3]].contiguous(), length=ld[[0, 3]].contiguous())
+    ys = ys.clone()
+    assert torch.equal(ys, y[[0, 3]])
+    # (6) and those two against the CPU oracle at full depth
+    want, wl = oc.encoder_forward(sd, cfg, x[[0, 3]], length[[0, 3]])
+    assert torch.equal(ls.cpu(), wl)
+    st = compare(ys.cpu(), want, ls)
+    assert st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, st
+    assert ctc_agreement(ys.cpu(), want, ls) >= 0.99
+
+
+def test_full_size_cfg4_properties_and_oracle_sample():
+    """BASELINE.json configs[3] at full size (Conformer-CTC Medium: d_model 256, 18 layers, 4 heads; 256 x 400 frames):
+    permutation equivariance bit for bit and 24 utterances against the CPU oracle."""
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=18, d_model=256, n_heads=4)
+    sd = oc.random_state_dict(cfg, 6)
+    B, T = 256, 400
+    g = torch.Generator().manual_seed(23)
+    lens = torch.randint(40, T + 1, (B,), generator=g).tolist()
+    lens[0], lens[1], lens[2] = T, 333, 41
+    x, length = oc.synthetic_batch(B, 80, T, lens, seed=12)
+    enc = build(cfg, sd, "bf16")
+    y, ylen = enc(audio_signal=x.cuda(), length=length.cuda())
+    y, ylen = y.clone(), ylen.clone()
+    perm = torch.randperm(B, generator=g).cuda()
+    yp, lp = enc(audio_signal=x.cuda()[perm].contiguous(), length=length.cuda()[perm].contiguous())
+    assert torch.equal(lp, ylen[perm]) and torch.equal(yp, y[perm])
+    n = 24  # ~1500 valid frames: one frame is < 0.1 % of the agreement statistic
+    want, wl = oc.encoder_forward(sd, cfg, x[:n], length[:n])
+    assert torch.equal(ylen[:n].cpu(), wl)
+    st = compare(y[:n].cpu(), want, ylen[:n])
+    assert st["nan"] == 0 and st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, st
+    agree = ctc_agreement(y[:n].cpu(), want, ylen[:n])
+    assert agree >= 0.99, (agree, st)
+
+
+def test_full_size_cfg5_long_form_bf16_against_fp32_validation_path():
+    """BASELINE.json configs[4] at full size (1 x 5 min = 30000 frames, T' = 7500, Conformer-L): the CPU oracle needs
+    minutes there, so the bf16 product path is compared with the library's fp32 CUDA-core validation path (itself
+    pinned to 1e-4 against the reference at the sizes the oracle handles), plus encoded_len and repeatability."""
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=17, d_model=512, n_heads=8)
+    sd = oc.random_state_dict(cfg, 7)
+    x, length = oc.synthetic_batch(1, 80, 30000, [29991], seed=13)
+    enc = build(cfg, sd, "bf16")
+    y, ylen = enc(audio_signal=x.cuda(), length=length.cuda())
+    y = y.clone()
+    assert ylen.tolist() == [((29991 + 1) // 2 + 1) // 2] and y.shape == (1, 512, 7500)
+    y2, _ = enc(audio_signal=x.cuda(), length=length.cuda())
+    assert torch.equal(y2, y)
+    del enc
+    ref = build(cfg, sd, "fp32_validate")
+    w, wl = ref(audio_signal=x.cuda(), length=length.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(wl, ylen)
+    st = compare(y.cpu(), w.cpu(), ylen)
+    assert st["nan"] == 0 and st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, st
+    assert ctc_agreement(y.cpu(), w.cpu(), ylen) >= 0.99
