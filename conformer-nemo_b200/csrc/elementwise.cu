@@ -542,7 +542,7 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
     if (sms <= 0) sms = 148;
   }
   int blocks = (rows + 7) / 8;
-  if (blocks > 4 * sms) blocks = 4 * sms;  // 32 warps per SM, each looping over rows
+  if (blocks > 2 * sms) blocks = 2 * sms;  // two resident CTAs per SM (90 registers): one balanced wave, each warp looping over rows
 #define CFB_LN(T, NV)                                                                                            \
   launch_pdl(layernorm_kernel<T, NV>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, reinterpret_cast<T*>(out), rows, \
              d, lens, frames_per_seq)

@@ -1,1 +1,3 @@
-timeout 900 python -m pytest tests/test_gpu_encoder.py -x -q -m gpu --tb=short -p no:cacheprovider -k "full_size" --durations=5 2>&1 | grep -v "^E  \+where\|^E  \+and" | tail -25 | tee gpurun_out/r03c_fullsize.log
+python tools/bench_ln.py 2>&1 | head -1
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r03d_ln4.json 2> gpurun_out/r03d_ln4.err
+python tools/show_bench.py gpurun_out/r03d_ln4.json 2>/dev/null | grep "value\|norm"
