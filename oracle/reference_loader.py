@@ -149,3 +149,52 @@ def load_reference_filterbank_class():
         utils.logging = _logging.getLogger("nemo_stub")
     mod = importlib.import_module("nemo.collections.asr.parts.preprocessing.features")
     return mod.FilterbankFeatures
+
+
+def load_reference_rnnt_classes():
+    """Returns the reference ``(RNNTDecoder, RNNTJoint, GreedyBatchedRNNTInfer)`` classes (modules/rnnt.py:51,613;
+    parts/submodules/rnnt_greedy_decoding.py:358), executed unmodified.  The files import framework symbols that are
+    absent here: ``nemo.core.NeuralModule`` (stand-in: torch.nn.Module + the ``as_frozen`` context manager of
+    nemo/core/classes/module.py:67-84), ``nemo.core.classes.Typing`` (empty class) and ``typecheck`` (no-op)."""
+    load_reference_encoder_class()  # registers the stub packages and nemo.utils.logging
+    name = "nemo.collections.asr.parts.submodules.rnnt_greedy_decoding"
+    if name in sys.modules:
+        g = sys.modules[name]
+        r = sys.modules["nemo.collections.asr.modules.rnnt"]
+        return r.RNNTDecoder, r.RNNTJoint, g.GreedyBatchedRNNTInfer
+    import contextlib
+
+    import torch
+
+    class NeuralModule(torch.nn.Module):
+        def freeze(self):
+            for p in self.parameters():
+                p.requires_grad = False
+            self.eval()
+
+        def unfreeze(self):
+            for p in self.parameters():
+                p.requires_grad = True
+            self.train()
+
+        @contextlib.contextmanager
+        def as_frozen(self):
+            training = self.training
+            flags = {n: p.requires_grad for n, p in self.named_parameters()}
+            self.freeze()
+            try:
+                yield
+            finally:
+                for n, p in self.named_parameters():
+                    p.requires_grad = flags[n]
+                self.train(training)
+
+    sys.modules["nemo.core"].NeuralModule = NeuralModule
+    classes = sys.modules["nemo.core.classes"]
+    classes.typecheck = sys.modules["nemo.core.classes.common"].typecheck
+    classes.Typing = type("Typing", (), {})
+    for pkg in ("nemo.collections.common", "nemo.collections.common.parts"):
+        _stub_package(pkg, os.path.join(REFERENCE_ROOT, *pkg.split(".")))
+    r = importlib.import_module("nemo.collections.asr.modules.rnnt")
+    g = importlib.import_module(name)
+    return r.RNNTDecoder, r.RNNTJoint, g.GreedyBatchedRNNTInfer
