@@ -25,6 +25,7 @@ SYMBOLS = [
     "cfb_workspace_bytes", "cfb_forward", "cfb_debug_buffer", "cfb_set_profiling", "cfb_profile_report",
     "cfb_last_launch_count", "cfb_op_gemm", "cfb_op_gemm_ln", "cfb_op_gemm_lnt", "cfb_op_ctc_head", "cfb_ctc_head_scratch_bytes",
     "cfb_op_layernorm", "cfb_op_depthwise", "cfb_op_dw_pw2", "cfb_op_logmel", "cfb_op_rel_attention", "cfb_op_lengths",
+    "cfb_rnnt_greedy_scratch_bytes", "cfb_op_rnnt_greedy",
 ]
 
 
@@ -35,6 +36,16 @@ class CfbConfig(ctypes.Structure):
         ("subsampling_conv_channels", ctypes.c_int32), ("ff_expansion_factor", ctypes.c_int32),
         ("n_heads", ctypes.c_int32), ("conv_kernel_size", ctypes.c_int32), ("xscaling", ctypes.c_int32),
         ("precision", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5),
+    ]
+
+
+class CfbRnntWeights(ctypes.Structure):
+    _fp = ctypes.POINTER(ctypes.c_float)
+    _fields_ = [
+        ("enc_hidden", ctypes.c_int32), ("pred_hidden", ctypes.c_int32), ("joint_hidden", ctypes.c_int32),
+        ("num_classes_with_blank", ctypes.c_int32), ("activation", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3),
+        ("embed", _fp), ("w_ih", _fp), ("w_hh", _fp), ("b_ih", _fp), ("b_hh", _fp), ("w_pred", _fp), ("b_pred", _fp),
+        ("w_enc", _fp), ("b_enc", _fp), ("w_out", _fp), ("b_out", _fp),
     ]
 
 
@@ -83,9 +94,12 @@ def load_library() -> ctypes.CDLL:
         lib.cfb_op_dw_pw2.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
         lib.cfb_op_rel_attention.argtypes = [i32, vp, vp, i64, vp, vp, i32, i32, i32, i32, i32, vp]
         lib.cfb_op_lengths.argtypes = [vp, vp, i32, i32, i32, vp]
+        lib.cfb_rnnt_greedy_scratch_bytes.argtypes = [i32, i32, i32, i32, i32]
+        lib.cfb_op_rnnt_greedy.argtypes = [ctypes.POINTER(CfbRnntWeights), vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
+                                           vp, vp, vp, sz, vp]
         for name in SYMBOLS:
             fn = getattr(lib, name)
-            if name == "cfb_ctc_head_scratch_bytes":
+            if name in ("cfb_ctc_head_scratch_bytes", "cfb_rnnt_greedy_scratch_bytes"):
                 fn.restype = ctypes.c_size_t
             elif name not in ("cfb_destroy", "cfb_last_error"):
                 fn.restype = ctypes.c_int

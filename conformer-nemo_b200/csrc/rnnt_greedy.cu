@@ -1,0 +1,549 @@
+// Transducer greedy decode on the encoder output: the prediction network (Embedding + one LSTM
+// layer, modules/rnnt.py:190-283), the joint network (modules/rnnt.py:951-1008) and the greedy_batch loop
+// (parts/submodules/rnnt_greedy_decoding.py:454-616) as ONE persistent cooperative kernel.
+//
+// The reference runs ~15 small PyTorch kernels plus a host synchronisation (`blank_mask.all()`) per symbol step.  Here
+//   * joint.enc is applied to every frame up front by the tcgen05 GEMM (bf16 hi/lo split operands, fp32 accumulation:
+//     A' = [hi | hi | lo], W' = [hi | lo | hi], so the product keeps fp32-level accuracy),
+//   * one CTA per SM keeps ITS rows of the LSTM, joint.pred and joint_net weights in shared memory in fp32 for the whole
+//     decode (weight-stationary: 17.4 MB / 148 SMs = 133 KB per SM for the Conformer-Transducer sizes), so a step moves
+//     only activations (a few KB per utterance) through L2,
+//   * utterances advance in lock-step "iterations": every active utterance evaluates the joint at its own frame; the ones
+//     that emitted a symbol then run the LSTM cell and joint.pred.  An utterance that produced a blank keeps its
+//     prediction-network output (the reference recomputes the identical value), so the LSTM runs once per emitted symbol,
+//   * the per-utterance control state (frame, symbols at this frame, last label, ...) is replicated in every CTA and
+//     advanced deterministically from the one exchanged datum: the arg-max, combined across CTAs with a packed 64-bit
+//     atomicMax (value bits | inverted index => first index wins ties like torch.max),
+//   * phases are separated by a grid barrier (1 per blank-only iteration, 3 when something was emitted).
+#include <float.h>
+
+#include "../../include/cfb.h"
+#include "common.cuh"
+
+namespace cfb {
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxB = 256;  // utterances per launch (control state lives in shared memory)
+constexpr int kHardSymbolLimit = 4096;  // symbols per frame when max_symbols is unlimited (flag bit 1 if ever reached)
+
+struct RnntParams {
+  // sizes
+  int E, H, J, V1, act, B, T, max_symbols, max_tokens;
+  // weights (fp32, reference state_dict layout)
+  const float *embed, *w_ih, *w_hh, *b_ih, *b_hh, *w_pred, *b_pred, *w_out, *b_out;
+  // activations
+  const float* encp;  // (B*T, J) = joint.enc(encoded)
+  const int32_t* lens;
+  float* hbuf;   // [2][B][H]
+  float* predp;  // [B][J]
+  unsigned long long* slots;  // [3][kMaxB]
+  unsigned int* counter;
+  // outputs
+  int32_t *tokens, *timesteps, *n_tokens, *flags;
+  float *scores, *h_out, *c_out;
+  int umax, pmax, jmax;  // rows per CTA (ceil)
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int& target) {
+  target += gridDim.x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (ld_acquire_u32(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float act_fn(float x, int act) {
+  return act == 0 ? fmaxf(x, 0.f) : (act == 1 ? sigmoidf_(x) : tanhf(x));
+}
+__device__ __forceinline__ unsigned long long pack_key(float v, int idx) {
+  unsigned int u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return (static_cast<unsigned long long>(u) << 32) | static_cast<unsigned long long>(0xffffffffu - static_cast<unsigned int>(idx));
+}
+__device__ __forceinline__ void unpack_key(unsigned long long key, float* v, int* idx) {
+  unsigned int u = static_cast<unsigned int>(key >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  *v = __uint_as_float(u);
+  *idx = static_cast<int>(0xffffffffu - static_cast<unsigned int>(key & 0xffffffffu));
+}
+// rows [lo, hi) of `n` rows owned by CTA c of g
+__device__ __forceinline__ void row_range(int n, int c, int g, int* lo, int* hi) {
+  *lo = static_cast<int>(static_cast<long long>(n) * c / g);
+  *hi = static_cast<int>(static_cast<long long>(n) * (c + 1) / g);
+}
+
+// compact list of the indices b < B with flag[b] != 0, in ascending order (identical in every CTA); returns the count
+__device__ int build_list(const int* flag, int B, int* list, int* s_tmp) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const bool f = tid < B && flag[tid] != 0;
+  const unsigned int m = __ballot_sync(0xffffffffu, f);
+  if (lane == 0) s_tmp[w] = __popc(m);
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int i = 0; i < kWarps; ++i) {
+    const int cnt = s_tmp[i];
+    if (i < w) base += cnt;
+    total += cnt;
+  }
+  if (f) list[base + __popc(m & ((1u << lane) - 1u))] = tid;
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int H = p.H, J = p.J, V1 = p.V1, B = p.B, K2 = 2 * p.H;
+  const int blank = V1 - 1;
+
+  int u_lo, u_hi, p_lo, p_hi, j_lo, j_hi;
+  row_range(H, cta, G, &u_lo, &u_hi);
+  row_range(J, cta, G, &p_lo, &p_hi);
+  row_range(V1, cta, G, &j_lo, &j_hi);
+  const int nu = u_hi - u_lo, np = p_hi - p_lo, nj = j_hi - j_lo;
+
+  // ---- shared memory carve-up ------------------------------------------------------------------------------------
+  float* s_wl = smem;                                   // [umax][4][2H]  LSTM rows of my units: [w_ih row | w_hh row]
+  float* s_wp = s_wl + static_cast<size_t>(p.umax) * 4 * K2;  // [pmax][H]
+  float* s_wj = s_wp + static_cast<size_t>(p.pmax) * H;       // [jmax][J]
+  float* s_bl = s_wj + static_cast<size_t>(p.jmax) * J;       // [umax][4] b_ih + b_hh
+  float* s_c = s_bl + p.umax * 4;                             // [2][kMaxB][umax] cell state of my units
+  __shared__ unsigned long long s_best[kMaxB];
+  __shared__ double s_score[kMaxB];
+  __shared__ int s_t[kMaxB], s_sym[kMaxB], s_last[kMaxB], s_par[kMaxB], s_ntok[kMaxB], s_len[kMaxB];
+  __shared__ int s_active[kMaxB], s_emit[kMaxB], s_alist[kMaxB], s_elist[kMaxB];
+  __shared__ int s_tmp[kWarps];
+
+  // ---- load my weight rows (once) ----------------------------------------------------------------------------------
+  for (int i = tid; i < nu * 4 * (K2 / 4); i += kThreads) {
+    const int k4 = i % (K2 / 4), r = i / (K2 / 4), gate = r & 3, ul = r >> 2;
+    const int row = gate * H + u_lo + ul;
+    const float* src = k4 < H / 4 ? p.w_ih + static_cast<size_t>(row) * H + k4 * 4
+                                  : p.w_hh + static_cast<size_t>(row) * H + (k4 - H / 4) * 4;
+    reinterpret_cast<float4*>(s_wl)[i] = __ldg(reinterpret_cast<const float4*>(src));
+  }
+  for (int i = tid; i < nu * 4; i += kThreads) {
+    const int row = (i & 3) * H + u_lo + (i >> 2);
+    s_bl[i] = p.b_ih[row] + p.b_hh[row];
+  }
+  for (int i = tid; i < np * (H / 4); i += kThreads)
+    reinterpret_cast<float4*>(s_wp)[i] = __ldg(reinterpret_cast<const float4*>(p.w_pred + static_cast<size_t>(p_lo) * H) + i);
+  for (int i = tid; i < nj * (J / 4); i += kThreads)
+    reinterpret_cast<float4*>(s_wj)[i] = __ldg(reinterpret_cast<const float4*>(p.w_out + static_cast<size_t>(j_lo) * J) + i);
+  if (tid < kMaxB) {
+    const int len = tid < B ? min(max(p.lens[tid], 0), p.T) : 0;
+    s_len[tid] = len;
+    s_t[tid] = 0;
+    s_sym[tid] = 0;
+    s_last[tid] = blank;
+    s_par[tid] = 0;
+    s_ntok[tid] = 0;
+    s_score[tid] = 0.0;
+    s_active[tid] = len > 0;
+    s_emit[tid] = tid < B;  // the SOS step: every utterance needs joint.pred of its first prediction-network output
+  }
+  __syncthreads();
+
+  // ---- SOS: pending = LSTM(x = 0, h = 0, c = 0) = f(bias) for every utterance; committed state = 0 (hbuf[1] is zeroed) --
+  for (int i = tid; i < nu * B; i += kThreads) {
+    const int ul = i % nu, b = i / nu;
+    const float* bl = s_bl + ul * 4;
+    const float c1 = sigmoidf_(bl[0]) * tanhf(bl[2]);  // f * 0 + i * g
+    const float h1 = sigmoidf_(bl[3]) * tanhf(c1);
+    s_c[(0 * kMaxB + b) * p.umax + ul] = c1;
+    s_c[(1 * kMaxB + b) * p.umax + ul] = 0.f;
+    p.hbuf[(static_cast<size_t>(0) * B + b) * H + u_lo + ul] = h1;
+  }
+  unsigned int bar_target = 0;
+  int n_emit = build_list(s_emit, B, s_elist, s_tmp);
+  int n_active = build_list(s_active, B, s_alist, s_tmp);
+  grid_sync(p.counter, bar_target);
+
+  bool first = true;
+  for (unsigned int it = 0;; ++it) {
+    if (!first) {
+      // ---- joint: logits of my rows for every active utterance at its frame, arg-max ----------------------------------
+      if (tid < kMaxB) s_best[tid] = 0ull;
+      __syncthreads();
+      const int npairs = (n_active + 1) >> 1, nchunks = (nj + 3) >> 2;
+      for (int task = warp; task < npairs * nchunks; task += kWarps) {
+        const int pr = task % npairs, ch = task / npairs;
+        const int b0 = s_alist[2 * pr], b1 = (2 * pr + 1 < n_active) ? s_alist[2 * pr + 1] : b0;
+        const float* e0 = p.encp + (static_cast<size_t>(b0) * p.T + s_t[b0]) * J;
+        const float* e1 = p.encp + (static_cast<size_t>(b1) * p.T + s_t[b1]) * J;
+        const float* g0 = p.predp + static_cast<size_t>(b0) * J;
+        const float* g1 = p.predp + static_cast<size_t>(b1) * J;
+        const int r0 = ch * 4;
+        float acc[4][2] = {};
+        for (int k4 = lane; k4 < J / 4; k4 += 32) {
+          float4 z0 = __ldg(reinterpret_cast<const float4*>(e0) + k4), z1 = __ldg(reinterpret_cast<const float4*>(e1) + k4);
+          const float4 q0 = ldcg4(g0 + k4 * 4), q1 = ldcg4(g1 + k4 * 4);
+          z0.x = act_fn(z0.x + q0.x, p.act), z0.y = act_fn(z0.y + q0.y, p.act);
+          z0.z = act_fn(z0.z + q0.z, p.act), z0.w = act_fn(z0.w + q0.w, p.act);
+          z1.x = act_fn(z1.x + q1.x, p.act), z1.y = act_fn(z1.y + q1.y, p.act);
+          z1.z = act_fn(z1.z + q1.z, p.act), z1.w = act_fn(z1.w + q1.w, p.act);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int rr = min(r0 + r, nj - 1);
+            const float4 w = reinterpret_cast<const float4*>(s_wj)[rr * (J / 4) + k4];
+            acc[r][0] = dot4(w, z0, acc[r][0]);
+            acc[r][1] = dot4(w, z1, acc[r][1]);
+          }
+        }
+        unsigned long long k0 = 0ull, k1 = 0ull;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float a0 = warp_sum(acc[r][0]), a1 = warp_sum(acc[r][1]);
+          if (r0 + r < nj) {
+            const int row = j_lo + r0 + r;
+            const float bias = __ldg(p.b_out + row);
+            const unsigned long long c0 = pack_key(a0 + bias, row), c1 = pack_key(a1 + bias, row);
+            k0 = c0 > k0 ? c0 : k0;
+            k1 = c1 > k1 ? c1 : k1;
+          }
+        }
+        if (lane == 0) atomicMax(&s_best[b0], k0);
+        if (lane == 1 && b1 != b0) atomicMax(&s_best[b1], k1);
+      }
+      __syncthreads();
+      if (nj > 0 && tid < n_active) {
+        const int b = s_alist[tid];
+        atomicMax(&p.slots[(it % 3) * kMaxB + b], s_best[b]);
+      }
+      grid_sync(p.counter, bar_target);
+
+      // ---- control update (replicated in every CTA) ---------------------------------------------------------------------
+      if (tid < kMaxB) {
+        int emit = 0;
+        if (tid < B && s_active[tid]) {
+          float v;
+          int k;
+          unpack_key(__ldcg(&p.slots[(it % 3) * kMaxB + tid]), &v, &k);
+          int t = s_t[tid], sym = s_sym[tid];
+          if (k == blank) {
+            ++t;
+            sym = 0;
+          } else {
+            emit = 1;
+            const int n = s_ntok[tid];
+            if (cta == 0) {
+              if (n < p.max_tokens) {
+                p.tokens[static_cast<size_t>(tid) * p.max_tokens + n] = k;
+                p.timesteps[static_cast<size_t>(tid) * p.max_tokens + n] = t;
+              } else {
+                atomicOr(p.flags, 1);
+              }
+              s_score[tid] += static_cast<double>(v);
+            }
+            s_ntok[tid] = n + 1;
+            s_last[tid] = k;
+            if (++sym >= (p.max_symbols > 0 ? p.max_symbols : kHardSymbolLimit)) {
+              if (p.max_symbols <= 0 && cta == 0) atomicOr(p.flags, 2);  // runaway emission: the reference would not return
+              ++t;
+              sym = 0;
+            }
+          }
+          s_t[tid] = t;
+          s_sym[tid] = sym;
+          s_active[tid] = t < s_len[tid];
+        }
+        s_emit[tid] = emit;
+        if (cta == 0) p.slots[((it + 2) % 3) * kMaxB + tid] = 0ull;
+      }
+      __syncthreads();
+      n_emit = build_list(s_emit, B, s_elist, s_tmp);
+      n_active = build_list(s_active, B, s_alist, s_tmp);
+
+      // ---- LSTM cell for the utterances that emitted: commit the pending state, compute the next one -----------------------
+      if (n_emit > 0) {
+        const int npe = (n_emit + 1) >> 1;
+        for (int task = warp; task < npe * nu; task += kWarps) {
+          const int pr = task % npe, ul = task / npe;
+          const int b0 = s_elist[2 * pr], b1 = (2 * pr + 1 < n_emit) ? s_elist[2 * pr + 1] : b0;
+          const float* x0 = p.embed + static_cast<size_t>(s_last[b0]) * H;
+          const float* x1 = p.embed + static_cast<size_t>(s_last[b1]) * H;
+          const float* h0 = p.hbuf + (static_cast<size_t>(s_par[b0]) * B + b0) * H;
+          const float* h1 = p.hbuf + (static_cast<size_t>(s_par[b1]) * B + b1) * H;
+          const float4* w = reinterpret_cast<const float4*>(s_wl) + static_cast<size_t>(ul) * 4 * (K2 / 4);
+          float acc[4][2] = {};
+          for (int k4 = lane; k4 < K2 / 4; k4 += 32) {
+            float4 a0, a1;
+            if (k4 < H / 4) {
+              a0 = __ldg(reinterpret_cast<const float4*>(x0) + k4);
+              a1 = __ldg(reinterpret_cast<const float4*>(x1) + k4);
+            } else {
+              a0 = ldcg4(h0 + (k4 - H / 4) * 4);
+              a1 = ldcg4(h1 + (k4 - H / 4) * 4);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 wv = w[g * (K2 / 4) + k4];
+              acc[g][0] = dot4(wv, a0, acc[g][0]);
+              acc[g][1] = dot4(wv, a1, acc[g][1]);
+            }
+          }
+          float gt[4][2];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            gt[g][0] = warp_sum(acc[g][0]) + s_bl[ul * 4 + g];
+            gt[g][1] = warp_sum(acc[g][1]) + s_bl[ul * 4 + g];
+          }
+          if (lane < 2 && (lane == 0 || b1 != b0)) {
+            const int b = lane == 0 ? b0 : b1;
+            const float gi = lane ? gt[0][1] : gt[0][0], gf = lane ? gt[1][1] : gt[1][0];
+            const float gg = lane ? gt[2][1] : gt[2][0], go = lane ? gt[3][1] : gt[3][0];
+            const int par = s_par[b];
+            const float c_old = s_c[(par * kMaxB + b) * p.umax + ul];
+            const float c_new = sigmoidf_(gf) * c_old + sigmoidf_(gi) * tanhf(gg);
+            const float h_new = sigmoidf_(go) * tanhf(c_new);
+            s_c[((par ^ 1) * kMaxB + b) * p.umax + ul] = c_new;
+            p.hbuf[(static_cast<size_t>(par ^ 1) * B + b) * H + u_lo + ul] = h_new;
+          }
+        }
+        __syncthreads();
+        if (tid < n_emit) s_par[s_elist[tid]] ^= 1;
+        grid_sync(p.counter, bar_target);
+      }
+      if (n_active == 0) break;
+    }
+    first = false;
+
+    // ---- joint.pred of the new prediction-network outputs -------------------------------------------------------------------
+    if (n_emit > 0) {
+      const int npe = (n_emit + 1) >> 1, nchunks = (np + 3) >> 2;
+      for (int task = warp; task < npe * nchunks; task += kWarps) {
+        const int pr = task % npe, ch = task / npe;
+        const int b0 = s_elist[2 * pr], b1 = (2 * pr + 1 < n_emit) ? s_elist[2 * pr + 1] : b0;
+        const float* h0 = p.hbuf + (static_cast<size_t>(s_par[b0]) * B + b0) * H;
+        const float* h1 = p.hbuf + (static_cast<size_t>(s_par[b1]) * B + b1) * H;
+        const int r0 = ch * 4;
+        float acc[4][2] = {};
+        for (int k4 = lane; k4 < H / 4; k4 += 32) {
+          const float4 a0 = ldcg4(h0 + k4 * 4), a1 = ldcg4(h1 + k4 * 4);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int rr = min(r0 + r, np - 1);
+            const float4 wv = reinterpret_cast<const float4*>(s_wp)[rr * (H / 4) + k4];
+            acc[r][0] = dot4(wv, a0, acc[r][0]);
+            acc[r][1] = dot4(wv, a1, acc[r][1]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float a0 = warp_sum(acc[r][0]), a1 = warp_sum(acc[r][1]);
+          if (r0 + r < np) {
+            const int row = p_lo + r0 + r;
+            const float bias = __ldg(p.b_pred + row);
+            if (lane == 0) p.predp[static_cast<size_t>(b0) * J + row] = a0 + bias;
+            if (lane == 1 && b1 != b0) p.predp[static_cast<size_t>(b1) * J + row] = a1 + bias;
+          }
+        }
+      }
+      grid_sync(p.counter, bar_target);
+    }
+    if (n_active == 0) break;
+  }
+
+  // ---- results: committed state = the buffer the pending one does not occupy ------------------------------------------------
+  for (int i = tid; i < nu * B; i += kThreads) {
+    const int ul = i % nu, b = i / nu;
+    p.c_out[static_cast<size_t>(b) * H + u_lo + ul] = s_c[((s_par[b] ^ 1) * kMaxB + b) * p.umax + ul];
+  }
+  for (int i = cta * kThreads + tid; i < B * H; i += G * kThreads) {
+    const int b = i / H, u = i % H;
+    p.h_out[i] = __ldcg(p.hbuf + (static_cast<size_t>(s_par[b] ^ 1) * B + b) * H + u);
+  }
+  if (cta == 0 && tid < B) {
+    p.n_tokens[tid] = s_ntok[tid];
+    p.scores[tid] = static_cast<float>(s_score[tid]);
+  }
+}
+
+// fp32 (rows, K) -> bf16 (rows, 3K) [hi | hi | lo]   (mode 0, activations)
+//                -> bf16 (rows, 3K) [hi | lo | hi]   (mode 1, weights)
+// bf16 input (mode 2): (rows, K) -> (rows, 2K) [x | x]
+__global__ void __launch_bounds__(256) split_bf16_kernel(const void* __restrict__ x, bf16* __restrict__ y, long long rows, int K,
+                                                         int mode) {
+  const long long n = rows * K;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / K;
+    const int k = static_cast<int>(i % K);
+    if (mode == 2) {
+      const bf16 v = reinterpret_cast<const bf16*>(x)[i];
+      y[r * 2 * K + k] = v;
+      y[r * 2 * K + K + k] = v;
+    } else {
+      const float v = reinterpret_cast<const float*>(x)[i];
+      const bf16 hi = __float2bfloat16_rn(v);
+      const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      bf16* o = y + r * 3 * K;
+      o[k] = hi;
+      o[K + k] = mode == 0 ? hi : lo;
+      o[2 * K + k] = mode == 0 ? lo : hi;
+    }
+  }
+}
+
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct RnntScratch {
+  size_t sync_off, sync_bytes, hbuf_off, hbuf_bytes, predp_off, encp_off, a_off, w_off, total;
+};
+RnntScratch rnnt_scratch_layout(int E, int H, int J, int B, int T) {
+  RnntScratch s;
+  const int Bc = B < kMaxB ? B : kMaxB;
+  size_t off = 0;
+  s.sync_off = off;
+  s.sync_bytes = align256(256 + sizeof(unsigned long long) * 3 * kMaxB);
+  off += s.sync_bytes;
+  s.hbuf_off = off;
+  s.hbuf_bytes = align256(sizeof(float) * 2 * Bc * H);
+  off += s.hbuf_bytes;
+  s.predp_off = off;
+  off += align256(sizeof(float) * Bc * J);
+  s.encp_off = off;
+  off += align256(sizeof(float) * static_cast<size_t>(B) * T * J);
+  s.a_off = off;
+  off += align256(sizeof(bf16) * static_cast<size_t>(B) * T * 3 * E);
+  s.w_off = off;
+  off += align256(sizeof(bf16) * static_cast<size_t>(J) * 3 * E);
+  s.total = off;
+  return s;
+}
+
+size_t rnnt_smem_bytes(int H, int J, int V1, int G, int* umax, int* pmax, int* jmax) {
+  *umax = (H + G - 1) / G;
+  *pmax = (J + G - 1) / G;
+  *jmax = (V1 + G - 1) / G;
+  return sizeof(float) * (static_cast<size_t>(*umax) * 4 * 2 * H + static_cast<size_t>(*pmax) * H + static_cast<size_t>(*jmax) * J +
+                          static_cast<size_t>(*umax) * 4 + static_cast<size_t>(2) * kMaxB * *umax);
+}
+
+}  // namespace
+}  // namespace cfb
+
+using namespace cfb;
+
+extern "C" {
+
+size_t cfb_rnnt_greedy_scratch_bytes(int enc_hidden, int pred_hidden, int joint_hidden, int B, int T) {
+  if (enc_hidden < 1 || pred_hidden < 1 || joint_hidden < 1 || B < 1 || T < 1) return 0;
+  return rnnt_scratch_layout(enc_hidden, pred_hidden, joint_hidden, B, T).total;
+}
+
+int cfb_op_rnnt_greedy(const cfb_rnnt_weights* w, const void* encoded, int x_dtype, const int32_t* encoded_len, int B, int T,
+                       int max_symbols, int max_tokens, int32_t* tokens, int32_t* timesteps, int32_t* n_tokens, float* scores,
+                       float* h_out, float* c_out, int32_t* flags, void* scratch, size_t scratch_bytes, cfb_stream stream) {
+  if (!w || !encoded || !encoded_len || !tokens || !timesteps || !n_tokens || !scores || !h_out || !c_out || !flags || !scratch)
+    return CFB_ERR_INVALID_ARG;
+  const int E = w->enc_hidden, H = w->pred_hidden, J = w->joint_hidden, V1 = w->num_classes_with_blank;
+  if (B < 1 || T < 1 || max_tokens < 1 || E < 8 || (E % 8) || H < 4 || (H % 4) || J < 4 || (J % 4) || V1 < 2)
+    return CFB_ERR_INVALID_ARG;
+  if (w->activation < 0 || w->activation > 2 || (x_dtype != CFB_F32 && x_dtype != CFB_BF16)) return CFB_ERR_INVALID_ARG;
+  if (!w->embed || !w->w_ih || !w->w_hh || !w->b_ih || !w->b_hh || !w->w_pred || !w->b_pred || !w->w_enc || !w->b_enc || !w->w_out ||
+      !w->b_out)
+    return CFB_ERR_INVALID_ARG;
+  const RnntScratch lay = rnnt_scratch_layout(E, H, J, B, T);
+  if (scratch_bytes < lay.total || (reinterpret_cast<uintptr_t>(scratch) & 255)) return CFB_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(scratch);
+
+  int dev = 0, sms = 0, max_smem = 0, coop = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return CFB_ERR_CUDA;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop || sms < 1) return CFB_ERR_UNSUPPORTED;
+  RnntParams p = {};
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, rnnt_greedy_kernel) != cudaSuccess) return CFB_ERR_CUDA;
+  const size_t smem = rnnt_smem_bytes(H, J, V1, sms, &p.umax, &p.pmax, &p.jmax);
+  if (smem + fa.sharedSizeBytes > static_cast<size_t>(max_smem)) return CFB_ERR_UNSUPPORTED;  // weights do not fit on chip
+  if (cudaFuncSetAttribute(rnnt_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+    return CFB_ERR_CUDA;
+
+  // joint.enc over every frame: encp = encoded W_enc^T + b_enc on the tensor cores with split operands
+  const bool xf32 = x_dtype == CFB_F32;
+  const long long M = static_cast<long long>(B) * T;
+  bf16* a_split = reinterpret_cast<bf16*>(ws + lay.a_off);
+  bf16* w_split = reinterpret_cast<bf16*>(ws + lay.w_off);
+  float* encp = reinterpret_cast<float*>(ws + lay.encp_off);
+  {
+    const long long n = M * E;
+    const int blocks = static_cast<int>((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    split_bf16_kernel<<<blocks, 256, 0, st>>>(encoded, a_split, M, E, xf32 ? 0 : 2);
+    split_bf16_kernel<<<(J * E + 255) / 256, 256, 0, st>>>(w->w_enc, w_split, J, E, 1);
+    GemmDesc g;
+    g.A = a_split;
+    g.lda = xf32 ? 3 * E : 2 * E;
+    g.W = w_split;
+    g.ldw = 3 * E;
+    g.M = static_cast<int>(M);
+    g.N = J;
+    g.K = xf32 ? 3 * E : 2 * E;
+    g.epi = EPI_LINEAR;
+    g.out_bf16 = false;
+    g.ep.bias = w->b_enc;
+    g.ep.out = encp;
+    g.ep.ldo = J;
+    std::string err;
+    if (launch_gemm_tc(g, st, &err) != 0) return CFB_ERR_CUDA;
+  }
+
+  for (int b0 = 0; b0 < B; b0 += kMaxB) {
+    const int Bc = B - b0 < kMaxB ? B - b0 : kMaxB;
+    if (cudaMemsetAsync(ws + lay.sync_off, 0, lay.sync_bytes + lay.hbuf_bytes, st) != cudaSuccess) return CFB_ERR_CUDA;
+    p.E = E, p.H = H, p.J = J, p.V1 = V1, p.act = w->activation, p.B = Bc, p.T = T;
+    p.max_symbols = max_symbols, p.max_tokens = max_tokens;
+    p.embed = w->embed, p.w_ih = w->w_ih, p.w_hh = w->w_hh, p.b_ih = w->b_ih, p.b_hh = w->b_hh;
+    p.w_pred = w->w_pred, p.b_pred = w->b_pred, p.w_out = w->w_out, p.b_out = w->b_out;
+    p.encp = encp + static_cast<size_t>(b0) * T * J;
+    p.lens = encoded_len + b0;
+    p.counter = reinterpret_cast<unsigned int*>(ws + lay.sync_off);
+    p.slots = reinterpret_cast<unsigned long long*>(ws + lay.sync_off + 256);
+    p.hbuf = reinterpret_cast<float*>(ws + lay.hbuf_off);
+    p.predp = reinterpret_cast<float*>(ws + lay.predp_off);
+    p.tokens = tokens + static_cast<size_t>(b0) * max_tokens;
+    p.timesteps = timesteps + static_cast<size_t>(b0) * max_tokens;
+    p.n_tokens = n_tokens + b0;
+    p.scores = scores + b0;
+    p.h_out = h_out + static_cast<size_t>(b0) * H;
+    p.c_out = c_out + static_cast<size_t>(b0) * H;
+    p.flags = flags;
+    void* args[] = {&p};
+    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rnnt_greedy_kernel), dim3(sms), dim3(kThreads), args, smem, st) !=
+        cudaSuccess)
+      return CFB_ERR_CUDA;
+  }
+  return cudaGetLastError() == cudaSuccess ? CFB_OK : CFB_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -221,6 +221,37 @@ CFB_API size_t cfb_ctc_head_scratch_bytes(int M, int d, int v1);
 CFB_API int cfb_op_ctc_head(const void* x, int x_dtype, const void* W, const float* bias, int M, int d, int v1,
                     float* logprobs, int32_t* best, void* scratch, size_t scratch_bytes, cfb_stream stream);
 
+/* ---- Transducer greedy decode on the encoder output (the transducer recipes' consumer) -------
+ * RNNTDecoder.predict (modules/rnnt.py:190-283: Embedding with the blank as padding row + one LSTM layer), RNNTJoint.joint
+ * (modules/rnnt.py:951-1008) and GreedyBatchedRNNTInfer._greedy_decode_blank_as_pad
+ * (parts/submodules/rnnt_greedy_decoding.py:454-616) in one persistent cooperative kernel (csrc/rnnt_greedy.cu).
+ * All weight pointers are DEVICE fp32 tensors in the reference state_dict layout:
+ *   embed  prediction.embed.weight (V+1, H), row V (= blank) must be the zero padding row
+ *   w_ih / w_hh / b_ih / b_hh  prediction.dec_rnn.lstm.{weight_ih,weight_hh,bias_ih,bias_hh}_l0  (4H, H) / (4H)
+ *   w_pred (J, H), b_pred (J) = joint.pred;  w_enc (J, E), b_enc (J) = joint.enc;  w_out (V+1, J), b_out = joint.joint_net[-1]
+ * activation: 0 relu, 1 sigmoid, 2 tanh (rnnt.py:1026-1037). */
+typedef struct cfb_rnnt_weights {
+  int32_t enc_hidden, pred_hidden, joint_hidden, num_classes_with_blank, activation, reserved[3];
+  const float *embed, *w_ih, *w_hh, *b_ih, *b_hh, *w_pred, *b_pred, *w_enc, *b_enc, *w_out, *b_out;
+} cfb_rnnt_weights;
+
+CFB_API size_t cfb_rnnt_greedy_scratch_bytes(int enc_hidden, int pred_hidden, int joint_hidden, int B, int T);
+/*   encoded      (B, T, E) row-major = the contiguous encoder output, CFB_F32 or CFB_BF16;  encoded_len (B) int32
+ *   max_symbols  symbols per frame (decoding.greedy.max_symbols; <= 0: no limit)
+ *   tokens, timesteps (B, max_tokens) int32 = Hypothesis.y_sequence / .timestep;  n_tokens (B)
+ *   scores       (B) sum of the winning joint outputs (raw logits: the reference's CUDA branch, rnnt_greedy_decoding.py:181-183)
+ *   h_out, c_out (B, H) = Hypothesis.dec_state (the LSTM state after the last emitted symbol; zeros if none)
+ *   flags        (1) int32, caller-zeroed; bit 0 is set if some utterance produced more than max_tokens symbols
+ *                (n_tokens keeps counting, the surplus is not stored); bit 1 if max_symbols <= 0 and some frame emitted
+ *                4096 symbols (a runaway the reference would never return from; the frame is then advanced)
+ *   scratch      >= cfb_rnnt_greedy_scratch_bytes(...), 256-byte aligned.  Enqueue-only on `stream`; needs a device
+ *                that supports cooperative launches and whose SMs together hold the fp32 weights in shared memory
+ *                (CFB_ERR_UNSUPPORTED otherwise). */
+CFB_API int cfb_op_rnnt_greedy(const cfb_rnnt_weights* w, const void* encoded, int x_dtype, const int32_t* encoded_len, int B,
+                       int T, int max_symbols, int max_tokens, int32_t* tokens, int32_t* timesteps, int32_t* n_tokens,
+                       float* scores, float* h_out, float* c_out, int32_t* flags, void* scratch, size_t scratch_bytes,
+                       cfb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
