@@ -26,6 +26,9 @@ namespace {
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxB = 256;  // utterances per launch (control state lives in shared memory)
+constexpr int kStageFloats = 10240;  // 40 KB staging buffer for activation vectors (16 x 640)
+constexpr int kMaxTile = 16;
+constexpr int kStageRound = 5;  // float4 per thread and staging round: 5 x 512 x 4 floats = the whole staging buffer
 constexpr int kHardSymbolLimit = 4096;  // symbols per frame when max_symbols is unlimited (flag bit 1 if ever reached)
 
 struct RnntParams {
@@ -52,13 +55,19 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
+// Grid barrier (all CTAs are co-resident: cooperative launch).  counter[0] counts arrivals (monotonic), counter[64]
+// (another 128-byte line) is the release flag the last arriver publishes, so the spinning CTAs poll a line no atomic hits.
 __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int& target) {
   target += gridDim.x;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(counter, 1u);
-    while (ld_acquire_u32(counter) < target) {
+    const unsigned int old = atomicAdd(counter, 1u);
+    if (old + 1u == target) {
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + 64), "r"(target) : "memory");
+    } else {
+      while (ld_acquire_u32(counter + 64) < target) {
+      }
     }
     __threadfence();
   }
@@ -92,6 +101,43 @@ __device__ __forceinline__ void unpack_key(unsigned long long key, float* v, int
   *v = __uint_as_float(u);
   *idx = static_cast<int>(0xffffffffu - static_cast<unsigned int>(key & 0xffffffffu));
 }
+// acc[r][s] += sum_k w[r][k] * z_s[k] for 4 weight rows and 2 staged activation vectors (all in shared memory, K4 float4 each).
+// NI > 0: K4 == 32 * NI, fully unrolled (the shared-memory loads of an iteration are issued ahead of the FMAs of the previous one).
+template <int NI>
+__device__ __forceinline__ void tile_dot_body(const float4* __restrict__ w, const float4* __restrict__ w1, const float4* __restrict__ w2,
+                                              const float4* __restrict__ w3, const float4* __restrict__ z0,
+                                              const float4* __restrict__ z1, int K4, int lane, float acc[4][2]) {
+  auto step = [&](int k4) {
+    const float4 a0 = z0[k4], a1 = z1[k4];
+    const float4 v0 = w[k4], v1 = w1[k4], v2 = w2[k4], v3 = w3[k4];
+    acc[0][0] = dot4(v0, a0, acc[0][0]), acc[0][1] = dot4(v0, a1, acc[0][1]);
+    acc[1][0] = dot4(v1, a0, acc[1][0]), acc[1][1] = dot4(v1, a1, acc[1][1]);
+    acc[2][0] = dot4(v2, a0, acc[2][0]), acc[2][1] = dot4(v2, a1, acc[2][1]);
+    acc[3][0] = dot4(v3, a0, acc[3][0]), acc[3][1] = dot4(v3, a1, acc[3][1]);
+  };
+  if (NI > 0) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) step(lane + 32 * i);
+  } else {
+#pragma unroll 2
+    for (int k4 = lane; k4 < K4; k4 += 32) step(k4);
+  }
+}
+__device__ __forceinline__ void tile_dot(const float4* __restrict__ w, int row_stride4, int nrows, const float4* __restrict__ z0,
+                                         const float4* __restrict__ z1, int K4, int lane, float acc[4][2]) {
+  const float4* w1 = w + (nrows > 1 ? 1 : 0) * row_stride4;
+  const float4* w2 = w + (nrows > 2 ? 2 : 0) * row_stride4;
+  const float4* w3 = w + (nrows > 3 ? 3 : 0) * row_stride4;
+  if (K4 == 160) tile_dot_body<5>(w, w1, w2, w3, z0, z1, K4, lane, acc);         // 640 (the transducer recipes' hidden sizes)
+  else if (K4 == 320) tile_dot_body<10>(w, w1, w2, w3, z0, z1, K4, lane, acc);   // 1280 = [x | h]
+  else tile_dot_body<0>(w, w1, w2, w3, z0, z1, K4, lane, acc);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    acc[r][0] = warp_sum(acc[r][0]);
+    acc[r][1] = warp_sum(acc[r][1]);
+  }
+}
+
 // rows [lo, hi) of `n` rows owned by CTA c of g
 __device__ __forceinline__ void row_range(int n, int c, int g, int* lo, int* hi) {
   *lo = static_cast<int>(static_cast<long long>(n) * c / g);
@@ -135,6 +181,10 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
   float* s_wj = s_wp + static_cast<size_t>(p.pmax) * H;       // [jmax][J]
   float* s_bl = s_wj + static_cast<size_t>(p.jmax) * J;       // [umax][4] b_ih + b_hh
   float* s_c = s_bl + p.umax * 4;                             // [2][kMaxB][umax] cell state of my units
+  float4* s_stage = reinterpret_cast<float4*>(s_c + ((static_cast<size_t>(2) * kMaxB * p.umax + 3) / 4) * 4);  // kStageFloats
+  const int J4 = J / 4, H4 = H / 4, K24 = K2 / 4;
+  const int tile_j = min(kMaxTile, kStageFloats / J) & ~1, tile_l = min(kMaxTile, kStageFloats / K2) & ~1,
+            tile_p = min(kMaxTile, kStageFloats / H) & ~1;  // utterances staged at a time (even: tasks take pairs)
   __shared__ unsigned long long s_best[kMaxB];
   __shared__ double s_score[kMaxB];
   __shared__ int s_t[kMaxB], s_sym[kMaxB], s_last[kMaxB], s_par[kMaxB], s_ntok[kMaxB], s_len[kMaxB];
@@ -187,57 +237,80 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
   grid_sync(p.counter, bar_target);
 
   bool first = true;
+  // phase clocks of CTA 0 (cycles; bytes 64..191 of the sync header): joint, barrier, control, lstm, barrier, pred, barrier
+  unsigned long long* timers = reinterpret_cast<unsigned long long*>(p.counter + 16);
+  long long tk = clock64();
+#define RNNT_TICK(slot)                                   \
+  if (cta == 0 && tid == 0) {                             \
+    const long long now = clock64();                      \
+    timers[slot] += static_cast<unsigned long long>(now - tk); \
+    tk = now;                                             \
+  }
   for (unsigned int it = 0;; ++it) {
     if (!first) {
       // ---- joint: logits of my rows for every active utterance at its frame, arg-max ----------------------------------
+      RNNT_TICK(7)
       if (tid < kMaxB) s_best[tid] = 0ull;
       __syncthreads();
-      const int npairs = (n_active + 1) >> 1, nchunks = (nj + 3) >> 2;
-      for (int task = warp; task < npairs * nchunks; task += kWarps) {
-        const int pr = task % npairs, ch = task / npairs;
-        const int b0 = s_alist[2 * pr], b1 = (2 * pr + 1 < n_active) ? s_alist[2 * pr + 1] : b0;
-        const float* e0 = p.encp + (static_cast<size_t>(b0) * p.T + s_t[b0]) * J;
-        const float* e1 = p.encp + (static_cast<size_t>(b1) * p.T + s_t[b1]) * J;
-        const float* g0 = p.predp + static_cast<size_t>(b0) * J;
-        const float* g1 = p.predp + static_cast<size_t>(b1) * J;
-        const int r0 = ch * 4;
-        float acc[4][2] = {};
-        for (int k4 = lane; k4 < J / 4; k4 += 32) {
-          float4 z0 = __ldg(reinterpret_cast<const float4*>(e0) + k4), z1 = __ldg(reinterpret_cast<const float4*>(e1) + k4);
-          const float4 q0 = ldcg4(g0 + k4 * 4), q1 = ldcg4(g1 + k4 * 4);
-          z0.x = act_fn(z0.x + q0.x, p.act), z0.y = act_fn(z0.y + q0.y, p.act);
-          z0.z = act_fn(z0.z + q0.z, p.act), z0.w = act_fn(z0.w + q0.w, p.act);
-          z1.x = act_fn(z1.x + q1.x, p.act), z1.y = act_fn(z1.y + q1.y, p.act);
-          z1.z = act_fn(z1.z + q1.z, p.act), z1.w = act_fn(z1.w + q1.w, p.act);
+      const int nchunks = (nj + 3) >> 2;
+      for (int s0 = 0; nj > 0 && s0 < n_active; s0 += tile_j) {
+        const int ns = min(tile_j, n_active - s0), total = ns * J4;
+        // stage z = act(enc_proj[b, t_b] + pred_proj[b]) of this tile: all loads of a round are issued before the first use
+        for (int base = 0; base < total; base += kThreads * kStageRound) {
+          float4 e[kStageRound], q[kStageRound];
+#pragma unroll
+          for (int u = 0; u < kStageRound; ++u) {
+            const int idx = base + u * kThreads + tid;
+            if (idx < total) {
+              const int bb = s_alist[s0 + idx / J4], k4 = idx % J4;
+              e[u] = __ldg(reinterpret_cast<const float4*>(p.encp + (static_cast<size_t>(bb) * p.T + s_t[bb]) * J) + k4);
+              q[u] = ldcg4(p.predp + static_cast<size_t>(bb) * J + k4 * 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kStageRound; ++u) {
+            const int idx = base + u * kThreads + tid;
+            if (idx < total) {
+              float4 z;
+              z.x = act_fn(e[u].x + q[u].x, p.act), z.y = act_fn(e[u].y + q[u].y, p.act);
+              z.z = act_fn(e[u].z + q[u].z, p.act), z.w = act_fn(e[u].w + q[u].w, p.act);
+              s_stage[idx] = z;
+            }
+          }
+        }
+        __syncthreads();
+        RNNT_TICK(8)
+        const int npairs = (ns + 1) >> 1;
+        for (int task = warp; task < npairs * nchunks; task += kWarps) {
+          const int pr = task % npairs, ch = task / npairs, r0 = ch * 4;
+          const int i0 = 2 * pr, i1 = (2 * pr + 1 < ns) ? 2 * pr + 1 : i0;
+          float acc[4][2] = {};
+          tile_dot(reinterpret_cast<const float4*>(s_wj) + r0 * J4, J4, nj - r0, s_stage + i0 * J4, s_stage + i1 * J4, J4, lane, acc);
+          unsigned long long k0 = 0ull, k1 = 0ull;
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            const int rr = min(r0 + r, nj - 1);
-            const float4 w = reinterpret_cast<const float4*>(s_wj)[rr * (J / 4) + k4];
-            acc[r][0] = dot4(w, z0, acc[r][0]);
-            acc[r][1] = dot4(w, z1, acc[r][1]);
+            if (r0 + r < nj) {
+              const int row = j_lo + r0 + r;
+              const float bias = __ldg(p.b_out + row);
+              const unsigned long long c0 = pack_key(acc[r][0] + bias, row), c1 = pack_key(acc[r][1] + bias, row);
+              k0 = c0 > k0 ? c0 : k0;
+              k1 = c1 > k1 ? c1 : k1;
+            }
           }
+          if (lane == 0) atomicMax(&s_best[s_alist[s0 + i0]], k0);
+          if (lane == 1 && i1 != i0) atomicMax(&s_best[s_alist[s0 + i1]], k1);
         }
-        unsigned long long k0 = 0ull, k1 = 0ull;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float a0 = warp_sum(acc[r][0]), a1 = warp_sum(acc[r][1]);
-          if (r0 + r < nj) {
-            const int row = j_lo + r0 + r;
-            const float bias = __ldg(p.b_out + row);
-            const unsigned long long c0 = pack_key(a0 + bias, row), c1 = pack_key(a1 + bias, row);
-            k0 = c0 > k0 ? c0 : k0;
-            k1 = c1 > k1 ? c1 : k1;
-          }
-        }
-        if (lane == 0) atomicMax(&s_best[b0], k0);
-        if (lane == 1 && b1 != b0) atomicMax(&s_best[b1], k1);
+        __syncthreads();
+        RNNT_TICK(9)
       }
       __syncthreads();
       if (nj > 0 && tid < n_active) {
         const int b = s_alist[tid];
         atomicMax(&p.slots[(it % 3) * kMaxB + b], s_best[b]);
       }
+      RNNT_TICK(0)
       grid_sync(p.counter, bar_target);
+      RNNT_TICK(1)
 
       // ---- control update (replicated in every CTA) ---------------------------------------------------------------------
       if (tid < kMaxB) {
@@ -280,56 +353,67 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
       __syncthreads();
       n_emit = build_list(s_emit, B, s_elist, s_tmp);
       n_active = build_list(s_active, B, s_alist, s_tmp);
+      {  // pull the joint.enc rows of the next two frames of every active utterance into L2 (one CTA per 128-byte line)
+        const int lines = (J * 4 + 127) / 128, total = n_active * 2 * lines;
+        for (int idx = cta * kThreads + tid; idx < total; idx += G * kThreads) {
+          const int ln = idx % lines, f = (idx / lines) & 1, bb = s_alist[idx / (2 * lines)];
+          const int t = s_t[bb] + 1 + f;
+          if (t < s_len[bb])
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.encp + (static_cast<size_t>(bb) * p.T + t) * J + ln * 32));
+        }
+      }
+      RNNT_TICK(2)
 
       // ---- LSTM cell for the utterances that emitted: commit the pending state, compute the next one -----------------------
       if (n_emit > 0) {
-        const int npe = (n_emit + 1) >> 1;
-        for (int task = warp; task < npe * nu; task += kWarps) {
-          const int pr = task % npe, ul = task / npe;
-          const int b0 = s_elist[2 * pr], b1 = (2 * pr + 1 < n_emit) ? s_elist[2 * pr + 1] : b0;
-          const float* x0 = p.embed + static_cast<size_t>(s_last[b0]) * H;
-          const float* x1 = p.embed + static_cast<size_t>(s_last[b1]) * H;
-          const float* h0 = p.hbuf + (static_cast<size_t>(s_par[b0]) * B + b0) * H;
-          const float* h1 = p.hbuf + (static_cast<size_t>(s_par[b1]) * B + b1) * H;
-          const float4* w = reinterpret_cast<const float4*>(s_wl) + static_cast<size_t>(ul) * 4 * (K2 / 4);
-          float acc[4][2] = {};
-          for (int k4 = lane; k4 < K2 / 4; k4 += 32) {
-            float4 a0, a1;
-            if (k4 < H / 4) {
-              a0 = __ldg(reinterpret_cast<const float4*>(x0) + k4);
-              a1 = __ldg(reinterpret_cast<const float4*>(x1) + k4);
-            } else {
-              a0 = ldcg4(h0 + (k4 - H / 4) * 4);
-              a1 = ldcg4(h1 + (k4 - H / 4) * 4);
+        for (int s0 = 0; nu > 0 && s0 < n_emit; s0 += tile_l) {
+          const int ns = min(tile_l, n_emit - s0), total = ns * K24;
+          // stage [embed(last label) | h] of the utterances of this tile
+          for (int base = 0; base < total; base += kThreads * kStageRound) {
+            float4 v[kStageRound];
+#pragma unroll
+            for (int u = 0; u < kStageRound; ++u) {
+              const int idx = base + u * kThreads + tid;
+              if (idx < total) {
+                const int bb = s_elist[s0 + idx / K24], k4 = idx % K24;
+                v[u] = k4 < H4 ? __ldg(reinterpret_cast<const float4*>(p.embed + static_cast<size_t>(s_last[bb]) * H) + k4)
+                               : ldcg4(p.hbuf + (static_cast<size_t>(s_par[bb]) * B + bb) * H + (k4 - H4) * 4);
+              }
             }
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 wv = w[g * (K2 / 4) + k4];
-              acc[g][0] = dot4(wv, a0, acc[g][0]);
-              acc[g][1] = dot4(wv, a1, acc[g][1]);
+            for (int u = 0; u < kStageRound; ++u) {
+              const int idx = base + u * kThreads + tid;
+              if (idx < total) s_stage[idx] = v[u];
             }
           }
-          float gt[4][2];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            gt[g][0] = warp_sum(acc[g][0]) + s_bl[ul * 4 + g];
-            gt[g][1] = warp_sum(acc[g][1]) + s_bl[ul * 4 + g];
+          __syncthreads();
+          const int npe = (ns + 1) >> 1;
+          for (int task = warp; task < npe * nu; task += kWarps) {
+            const int pr = task % npe, ul = task / npe;
+            const int i0 = 2 * pr, i1 = (2 * pr + 1 < ns) ? 2 * pr + 1 : i0;
+            float acc[4][2] = {};
+            tile_dot(reinterpret_cast<const float4*>(s_wl) + static_cast<size_t>(ul) * 4 * K24, K24, 4, s_stage + i0 * K24,
+                     s_stage + i1 * K24, K24, lane, acc);
+            if (lane < 2 && (lane == 0 || i1 != i0)) {
+              const int b = s_elist[s0 + (lane == 0 ? i0 : i1)];
+              const float* bl = s_bl + ul * 4;
+              const float gi = (lane ? acc[0][1] : acc[0][0]) + bl[0], gf = (lane ? acc[1][1] : acc[1][0]) + bl[1];
+              const float gg = (lane ? acc[2][1] : acc[2][0]) + bl[2], go = (lane ? acc[3][1] : acc[3][0]) + bl[3];
+              const int par = s_par[b];
+              const float c_old = s_c[(par * kMaxB + b) * p.umax + ul];
+              const float c_new = sigmoidf_(gf) * c_old + sigmoidf_(gi) * tanhf(gg);
+              const float h_new = sigmoidf_(go) * tanhf(c_new);
+              s_c[((par ^ 1) * kMaxB + b) * p.umax + ul] = c_new;
+              p.hbuf[(static_cast<size_t>(par ^ 1) * B + b) * H + u_lo + ul] = h_new;
+            }
           }
-          if (lane < 2 && (lane == 0 || b1 != b0)) {
-            const int b = lane == 0 ? b0 : b1;
-            const float gi = lane ? gt[0][1] : gt[0][0], gf = lane ? gt[1][1] : gt[1][0];
-            const float gg = lane ? gt[2][1] : gt[2][0], go = lane ? gt[3][1] : gt[3][0];
-            const int par = s_par[b];
-            const float c_old = s_c[(par * kMaxB + b) * p.umax + ul];
-            const float c_new = sigmoidf_(gf) * c_old + sigmoidf_(gi) * tanhf(gg);
-            const float h_new = sigmoidf_(go) * tanhf(c_new);
-            s_c[((par ^ 1) * kMaxB + b) * p.umax + ul] = c_new;
-            p.hbuf[(static_cast<size_t>(par ^ 1) * B + b) * H + u_lo + ul] = h_new;
-          }
+          __syncthreads();
         }
         __syncthreads();
         if (tid < n_emit) s_par[s_elist[tid]] ^= 1;
+        RNNT_TICK(3)
         grid_sync(p.counter, bar_target);
+        RNNT_TICK(4)
       }
       if (n_active == 0) break;
     }
@@ -337,36 +421,48 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
 
     // ---- joint.pred of the new prediction-network outputs -------------------------------------------------------------------
     if (n_emit > 0) {
-      const int npe = (n_emit + 1) >> 1, nchunks = (np + 3) >> 2;
-      for (int task = warp; task < npe * nchunks; task += kWarps) {
-        const int pr = task % npe, ch = task / npe;
-        const int b0 = s_elist[2 * pr], b1 = (2 * pr + 1 < n_emit) ? s_elist[2 * pr + 1] : b0;
-        const float* h0 = p.hbuf + (static_cast<size_t>(s_par[b0]) * B + b0) * H;
-        const float* h1 = p.hbuf + (static_cast<size_t>(s_par[b1]) * B + b1) * H;
-        const int r0 = ch * 4;
-        float acc[4][2] = {};
-        for (int k4 = lane; k4 < H / 4; k4 += 32) {
-          const float4 a0 = ldcg4(h0 + k4 * 4), a1 = ldcg4(h1 + k4 * 4);
+      const int nchunks = (np + 3) >> 2;
+      for (int s0 = 0; np > 0 && s0 < n_emit; s0 += tile_p) {
+        const int ns = min(tile_p, n_emit - s0), total = ns * H4;
+        for (int base = 0; base < total; base += kThreads * kStageRound) {
+          float4 v[kStageRound];
+#pragma unroll
+          for (int u = 0; u < kStageRound; ++u) {
+            const int idx = base + u * kThreads + tid;
+            if (idx < total) {
+              const int bb = s_elist[s0 + idx / H4];
+              v[u] = ldcg4(p.hbuf + (static_cast<size_t>(s_par[bb]) * B + bb) * H + (idx % H4) * 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kStageRound; ++u) {
+            const int idx = base + u * kThreads + tid;
+            if (idx < total) s_stage[idx] = v[u];
+          }
+        }
+        __syncthreads();
+        const int npe = (ns + 1) >> 1;
+        for (int task = warp; task < npe * nchunks; task += kWarps) {
+          const int pr = task % npe, ch = task / npe, r0 = ch * 4;
+          const int i0 = 2 * pr, i1 = (2 * pr + 1 < ns) ? 2 * pr + 1 : i0;
+          float acc[4][2] = {};
+          tile_dot(reinterpret_cast<const float4*>(s_wp) + r0 * H4, H4, np - r0, s_stage + i0 * H4, s_stage + i1 * H4, H4, lane, acc);
+          const int b0 = s_elist[s0 + i0], b1 = s_elist[s0 + i1];
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            const int rr = min(r0 + r, np - 1);
-            const float4 wv = reinterpret_cast<const float4*>(s_wp)[rr * (H / 4) + k4];
-            acc[r][0] = dot4(wv, a0, acc[r][0]);
-            acc[r][1] = dot4(wv, a1, acc[r][1]);
+            if (r0 + r < np) {
+              const int row = p_lo + r0 + r;
+              const float bias = __ldg(p.b_pred + row);
+              if (lane == 0) p.predp[static_cast<size_t>(b0) * J + row] = acc[r][0] + bias;
+              if (lane == 1 && i1 != i0) p.predp[static_cast<size_t>(b1) * J + row] = acc[r][1] + bias;
+            }
           }
         }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float a0 = warp_sum(acc[r][0]), a1 = warp_sum(acc[r][1]);
-          if (r0 + r < np) {
-            const int row = p_lo + r0 + r;
-            const float bias = __ldg(p.b_pred + row);
-            if (lane == 0) p.predp[static_cast<size_t>(b0) * J + row] = a0 + bias;
-            if (lane == 1 && b1 != b0) p.predp[static_cast<size_t>(b1) * J + row] = a1 + bias;
-          }
-        }
+        __syncthreads();
       }
+      RNNT_TICK(5)
       grid_sync(p.counter, bar_target);
+      RNNT_TICK(6)
     }
     if (n_active == 0) break;
   }
@@ -422,7 +518,7 @@ RnntScratch rnnt_scratch_layout(int E, int H, int J, int B, int T) {
   const int Bc = B < kMaxB ? B : kMaxB;
   size_t off = 0;
   s.sync_off = off;
-  s.sync_bytes = align256(256 + sizeof(unsigned long long) * 3 * kMaxB);
+  s.sync_bytes = align256(512 + sizeof(unsigned long long) * 3 * kMaxB);
   off += s.sync_bytes;
   s.hbuf_off = off;
   s.hbuf_bytes = align256(sizeof(float) * 2 * Bc * H);
@@ -444,7 +540,7 @@ size_t rnnt_smem_bytes(int H, int J, int V1, int G, int* umax, int* pmax, int* j
   *pmax = (J + G - 1) / G;
   *jmax = (V1 + G - 1) / G;
   return sizeof(float) * (static_cast<size_t>(*umax) * 4 * 2 * H + static_cast<size_t>(*pmax) * H + static_cast<size_t>(*jmax) * J +
-                          static_cast<size_t>(*umax) * 4 + static_cast<size_t>(2) * kMaxB * *umax);
+                          static_cast<size_t>(*umax) * 4 + (static_cast<size_t>(2) * kMaxB * *umax + 3) / 4 * 4 + kStageFloats);
 }
 
 }  // namespace
@@ -528,7 +624,7 @@ int cfb_op_rnnt_greedy(const cfb_rnnt_weights* w, const void* encoded, int x_dty
     p.encp = encp + static_cast<size_t>(b0) * T * J;
     p.lens = encoded_len + b0;
     p.counter = reinterpret_cast<unsigned int*>(ws + lay.sync_off);
-    p.slots = reinterpret_cast<unsigned long long*>(ws + lay.sync_off + 256);
+    p.slots = reinterpret_cast<unsigned long long*>(ws + lay.sync_off + 512);
     p.hbuf = reinterpret_cast<float*>(ws + lay.hbuf_off);
     p.predp = reinterpret_cast<float*>(ws + lay.predp_off);
     p.tokens = tokens + static_cast<size_t>(b0) * max_tokens;

@@ -223,6 +223,8 @@ class GreedyBatchedRNNTInfer:
                                         ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
         _lib.check(rc, None, "cfb_op_rnnt_greedy")
         out["_keepalive"] = (x, lens)
+        off = sptr - self._scratch.data_ptr()
+        out["phase_cycles"] = self._scratch[off + 64:off + 192].view(torch.int64)  # CTA 0's clocks per phase (debugging)
         return out
 
     @torch.no_grad()

@@ -65,6 +65,8 @@ def main():
     out = greedy.decode_arrays(xg, lg)
     torch.cuda.synchronize()
     n_tok = out["n_tokens"].cpu()
+    phases = dict(zip(["joint", "barrier_joint", "control", "lstm", "barrier_lstm", "pred", "barrier_pred", "loop", "joint_stage", "joint_compute"],
+                      out["phase_cycles"].cpu().tolist()))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(args.warmup):
         greedy.decode_arrays(xg, lg)
@@ -86,7 +88,8 @@ def main():
                                           mode="GreedyBatchedRNNTInfer.forward: decode + hypotheses on the host"),
                 config=dict(workload=f"Conformer-Transducer Large decoder/joint (512/640/640/1025), {B} x {T} frames, max_symbols 30",
                             encoder_output_dtype=args.dtype, blank_bias=bias, symbols_per_frame=symbols_per_frame),
-                symbols=int(n_tok.sum()), iterations=iters, us_per_iteration=ms * 1e3 / max(iters, 1), gpu_launches=5)
+                symbols=int(n_tok.sum()), iterations=iters, us_per_iteration=ms * 1e3 / max(iters, 1), gpu_launches=5,
+                phase_cycles_cta0=phases)
     if args.cpu_sample > 0:
         k = min(args.cpu_sample, B)
         torch.set_num_threads(os.cpu_count() or 1)
