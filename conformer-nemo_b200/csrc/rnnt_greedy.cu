@@ -353,15 +353,6 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
       __syncthreads();
       n_emit = build_list(s_emit, B, s_elist, s_tmp);
       n_active = build_list(s_active, B, s_alist, s_tmp);
-      {  // pull the joint.enc rows of the next two frames of every active utterance into L2 (one CTA per 128-byte line)
-        const int lines = (J * 4 + 127) / 128, total = n_active * 2 * lines;
-        for (int idx = cta * kThreads + tid; idx < total; idx += G * kThreads) {
-          const int ln = idx % lines, f = (idx / lines) & 1, bb = s_alist[idx / (2 * lines)];
-          const int t = s_t[bb] + 1 + f;
-          if (t < s_len[bb])
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.encp + (static_cast<size_t>(bb) * p.T + t) * J + ln * 32));
-        }
-      }
       RNNT_TICK(2)
 
       // ---- LSTM cell for the utterances that emitted: commit the pending state, compute the next one -----------------------

@@ -198,3 +198,56 @@ def load_reference_rnnt_classes():
     r = importlib.import_module("nemo.collections.asr.modules.rnnt")
     g = importlib.import_module(name)
     return r.RNNTDecoder, r.RNNTJoint, g.GreedyBatchedRNNTInfer
+
+
+def load_reference_collation():
+    """Returns ``(audio_to_text module, collections module)`` of the reference, executed unmodified:
+    ``data/audio_to_text.py`` (``_speech_collate_fn`` :48-99, ``BucketingIterator`` :1515-1533) and
+    ``common/parts/preprocessing/collections.py`` (``ASRAudioText`` manifest filtering :88-216).  Their imports that are
+    absent here (braceexpand, webdataset, frozendict, the text cleaners, tokenizers, nemo.core Dataset classes,
+    ``deprecated``) get inert stand-ins; none of them contributes to collation or manifest filtering."""
+    load_reference_filterbank_class()  # stub packages, nemo.utils.logging, librosa stand-in, features.py
+    name = "nemo.collections.asr.data.audio_to_text"
+    if name in sys.modules:
+        return sys.modules[name], sys.modules["nemo.collections.common.parts.preprocessing.collections"]
+    import torch
+
+    for pkg in ("nemo.collections.common", "nemo.collections.common.parts", "nemo.collections.common.parts.preprocessing",
+                "nemo.collections.asr.data"):
+        if pkg not in sys.modules:
+            _stub_package(pkg, os.path.join(REFERENCE_ROOT, *pkg.split(".")))
+    for mod_name in ("braceexpand", "webdataset"):
+        if mod_name not in sys.modules:
+            sys.modules[mod_name] = types.ModuleType(mod_name)
+    if "frozendict" not in sys.modules:
+        fd = types.ModuleType("frozendict")
+        fd.frozendict = dict
+        sys.modules["frozendict"] = fd
+    cleaners = types.ModuleType("nemo.collections.common.parts.preprocessing.cleaners")
+    cleaners.clean_text = lambda s, *a, **k: s
+    sys.modules[cleaners.__name__] = cleaners
+    tok = types.ModuleType("nemo.collections.common.tokenizers")
+    tok.TokenizerSpec = type("TokenizerSpec", (), {})
+    tok.AggregateTokenizer = type("AggregateTokenizer", (), {})
+    sys.modules[tok.__name__] = tok
+    sys.modules["nemo.collections.common"].tokenizers = tok
+    classes = sys.modules["nemo.core.classes"]
+    classes.Dataset = torch.utils.data.Dataset
+    classes.IterableDataset = torch.utils.data.IterableDataset
+    if not hasattr(classes, "typecheck"):
+        classes.typecheck = sys.modules["nemo.core.classes.common"].typecheck
+    dec = types.ModuleType("nemo.utils.decorators")
+
+    def deprecated(*_a, **_k):
+        return lambda fn: fn
+
+    dec.deprecated = deprecated
+    sys.modules[dec.__name__] = dec
+    utils = sys.modules["nemo.utils"]
+    if not hasattr(utils.logging, "info"):
+        import logging as _logging
+
+        utils.logging = _logging.getLogger("nemo_stub")
+    coll = importlib.import_module("nemo.collections.common.parts.preprocessing.collections")
+    a2t = importlib.import_module(name)
+    return a2t, coll
