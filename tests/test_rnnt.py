@@ -221,3 +221,38 @@ def test_gpu_full_size_properties():
     big = _decode_gpu(greedy, x[:, :, :60].repeat(reps, 1, 1), torch.clamp(lens, max=60).repeat(reps))
     for i in range(B, reps * B):
         assert key(big[i])[:2] == key(big[i % B])[:2]
+
+
+@pytest.mark.gpu
+def test_gpu_transducer_pipeline_waveform_to_hypotheses():
+    """The whole transducer inference path on the device: collation service -> log-mel kernels -> encoder kernels ->
+    greedy decode kernel; the decode is checked against the oracle fed with the SAME encoder output, the lengths against
+    the encoder's."""
+    from oracle import conformer_oracle as oc
+    from oracle import frontend_oracle as fo
+
+    x, lengths = fo.synthetic_waveforms(5, 32000, [32000, 20000, 9000, 32000, 16000], seed=7)
+    svc = cn.CollationService([int(v) for v in lengths], lambda i: (x[i, :int(lengths[i])], torch.zeros(0, dtype=torch.int64)),
+                              max_batch=8, bucket_frames=400, device="cuda")
+    pre = cn.AudioToMelSpectrogramPreprocessor(sample_rate=16000, normalize="per_feature", window_size=0.025,
+                                               window_stride=0.01, window="hann", features=80, n_fft=512, dither=0.0,
+                                               pad_to=0).cuda()
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=2, d_model=256, n_heads=4)
+    enc = cn.ConformerEncoder(feat_in=80, n_layers=2, d_model=256, n_heads=4)
+    enc.load_state_dict(oc.random_state_dict(cfg, 4), strict=False)
+    enc = enc.cuda().eval()
+    dims = (256, 320, 320, 128)
+    dec_sd, joint_sd = ro.random_rnnt_state_dicts(*dims, seed=51, blank_bias=0.4)
+    _, _, greedy = build_modules(dims, dec_sd, joint_sd, "relu", 10, "cuda")
+    seen = 0
+    for batch in svc:
+        svc.wait(batch)
+        feats, flen = pre(input_signal=batch.audio_signal, length=batch.audio_lengths)
+        encoded, elen = enc(audio_signal=feats, length=flen)
+        (hyps,) = greedy(encoder_output=encoded, encoded_lengths=elen)
+        want = ro.rnnt_greedy_decode(encoded.float().cpu(), elen.cpu(), dec_sd, joint_sd, 10, "relu", False)
+        assert _compare(hyps, want) == []
+        for h, n in zip(hyps, elen.cpu().tolist()):
+            assert int(h.length) == n and (len(h.timestep) == 0 or max(h.timestep) < n)
+        seen += len(hyps)
+    assert seen == 5
