@@ -25,9 +25,9 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxB = 256;  // utterances per launch (control state lives in shared memory)
-constexpr int kStageFloats = 10240;  // 40 KB staging buffer for activation vectors (16 x 640)
-constexpr int kMaxTile = 16;
+constexpr int kMaxB = 128;  // utterances per launch (control state lives in shared memory)
+constexpr int kMaxTile = 32;  // utterances staged in shared memory at a time (the staging buffer takes what the weights leave)
+constexpr int kJointRound = 3;  // (e0, e1, q) float4 triples per thread and joint staging round
 constexpr int kStageRound = 5;  // float4 per thread and staging round: 5 x 512 x 4 floats = the whole staging buffer
 constexpr int kHardSymbolLimit = 4096;  // symbols per frame when max_symbols is unlimited (flag bit 1 if ever reached)
 
@@ -41,12 +41,13 @@ struct RnntParams {
   const int32_t* lens;
   float* hbuf;   // [2][B][H]
   float* predp;  // [B][J]
-  unsigned long long* slots;  // [3][kMaxB]
+  unsigned long long* slots;  // [3][2][kMaxB]
   unsigned int* counter;
   // outputs
   int32_t *tokens, *timesteps, *n_tokens, *flags;
   float *scores, *h_out, *c_out;
   int umax, pmax, jmax;  // rows per CTA (ceil)
+  int stage_floats;      // size of the activation staging buffer
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -58,18 +59,20 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 // Grid barrier (all CTAs are co-resident: cooperative launch).  counter[0] counts arrivals (monotonic), counter[64]
 // (another 128-byte line) is the release flag the last arriver publishes, so the spinning CTAs poll a line no atomic hits.
 __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int& target) {
+  // Release/acquire chain instead of two full fences: bar.sync orders the CTA's writes before thread 0's acq_rel
+  // arrival (cumulative), the last arriver publishes the flag with a release store, pollers acquire it, bar.sync hands
+  // the ordering to the rest of the CTA.  Every mutable global datum is read with ld.global.cg (never from L1).
   target += gridDim.x;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int old = atomicAdd(counter, 1u);
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
     if (old + 1u == target) {
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(counter + 64), "r"(target) : "memory");
     } else {
       while (ld_acquire_u32(counter + 64) < target) {
       }
     }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -138,6 +141,44 @@ __device__ __forceinline__ void tile_dot(const float4* __restrict__ w, int row_s
   }
 }
 
+// 8 weight rows x 4 staged activation vectors: acc[r * 4 + s] += sum_k w[r][k] * z_s[k] over this lane's k, then a transposing
+// butterfly (31 shuffles instead of 160) leaves the warp total of accumulator i in lane i: lane = row * 4 + utterance.
+template <int NI>
+__device__ __forceinline__ float tile_dot84(const float4* __restrict__ w, int row_stride4, int nrows, const float4* __restrict__ z,
+                                            int z_stride4, const int zi[4], int K4, int lane) {
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  auto step = [&](int k4) {
+    float4 a[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) a[s] = z[zi[s] * z_stride4 + k4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float4 v = w[(r < nrows ? r : 0) * row_stride4 + k4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) acc[r * 4 + s] = dot4(v, a[s], acc[r * 4 + s]);
+    }
+  };
+  if (NI > 0) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) step(lane + 32 * i);
+  } else {
+    for (int k4 = lane; k4 < K4; k4 += 32) step(k4);
+  }
+#pragma unroll
+  for (int half = 16; half > 0; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? acc[i] : acc[i + half];
+      const float keep = up ? acc[i + half] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return acc[0];
+}
+
 // rows [lo, hi) of `n` rows owned by CTA c of g
 __device__ __forceinline__ void row_range(int n, int c, int g, int* lo, int* hi) {
   *lo = static_cast<int>(static_cast<long long>(n) * c / g);
@@ -180,12 +221,13 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
   float* s_wp = s_wl + static_cast<size_t>(p.umax) * 4 * K2;  // [pmax][H]
   float* s_wj = s_wp + static_cast<size_t>(p.pmax) * H;       // [jmax][J]
   float* s_bl = s_wj + static_cast<size_t>(p.jmax) * J;       // [umax][4] b_ih + b_hh
-  float* s_c = s_bl + p.umax * 4;                             // [2][kMaxB][umax] cell state of my units
-  float4* s_stage = reinterpret_cast<float4*>(s_c + ((static_cast<size_t>(2) * kMaxB * p.umax + 3) / 4) * 4);  // kStageFloats
+  float* s_c = s_bl + p.umax * 4;                             // [2][B][umax] cell state of my units
+  float4* s_stage = reinterpret_cast<float4*>(s_c + ((static_cast<size_t>(2) * B * p.umax + 3) / 4) * 4);  // p.stage_floats
   const int J4 = J / 4, H4 = H / 4, K24 = K2 / 4;
-  const int tile_j = min(kMaxTile, kStageFloats / J) & ~1, tile_l = min(kMaxTile, kStageFloats / K2) & ~1,
-            tile_p = min(kMaxTile, kStageFloats / H) & ~1;  // utterances staged at a time (even: tasks take pairs)
-  __shared__ unsigned long long s_best[kMaxB];
+  // utterances staged at a time: joint tasks take groups of 4, the LSTM / pred tasks pairs
+  const int tile_j = min(kMaxTile, p.stage_floats / J) & ~3, tile_l = min(kMaxTile, p.stage_floats / K2) & ~1,
+            tile_p = min(kMaxTile, p.stage_floats / H) & ~1;
+  __shared__ unsigned long long s_best[2 * kMaxB];  // [frame 0 | frame 1][utterance]
   __shared__ double s_score[kMaxB];
   __shared__ int s_t[kMaxB], s_sym[kMaxB], s_last[kMaxB], s_par[kMaxB], s_ntok[kMaxB], s_len[kMaxB];
   __shared__ int s_active[kMaxB], s_emit[kMaxB], s_alist[kMaxB], s_elist[kMaxB];
@@ -227,8 +269,8 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
     const float* bl = s_bl + ul * 4;
     const float c1 = sigmoidf_(bl[0]) * tanhf(bl[2]);  // f * 0 + i * g
     const float h1 = sigmoidf_(bl[3]) * tanhf(c1);
-    s_c[(0 * kMaxB + b) * p.umax + ul] = c1;
-    s_c[(1 * kMaxB + b) * p.umax + ul] = 0.f;
+    s_c[(0 * B + b) * p.umax + ul] = c1;
+    s_c[(1 * B + b) * p.umax + ul] = 0.f;
     p.hbuf[(static_cast<size_t>(0) * B + b) * H + u_lo + ul] = h1;
   }
   unsigned int bar_target = 0;
@@ -250,63 +292,72 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
     if (!first) {
       // ---- joint: logits of my rows for every active utterance at its frame, arg-max ----------------------------------
       RNNT_TICK(7)
-      if (tid < kMaxB) s_best[tid] = 0ull;
+      if (cta == 0 && tid == 0) timers[10] += 1;  // lock-step iterations
+      // Two frames per utterance are evaluated with the same prediction-network output: if the first is blank (the common
+      // case) the second is already the answer for the next frame, so a lock-step iteration consumes up to two frames.
+      if (tid < 2 * kMaxB) s_best[tid] = 0ull;
       __syncthreads();
-      const int nchunks = (nj + 3) >> 2;
-      for (int s0 = 0; nj > 0 && s0 < n_active; s0 += tile_j) {
-        const int ns = min(tile_j, n_active - s0), total = ns * J4;
-        // stage z = act(enc_proj[b, t_b] + pred_proj[b]) of this tile: all loads of a round are issued before the first use
-        for (int base = 0; base < total; base += kThreads * kStageRound) {
-          float4 e[kStageRound], q[kStageRound];
+      const int nchunks = (nj + 7) >> 3;
+      const int tile_s = tile_j >> 1;  // utterances per tile (two staged vectors each)
+      for (int s0 = 0; nj > 0 && s0 < n_active; s0 += tile_s) {
+        const int ns = min(tile_s, n_active - s0), total = ns * J4;
+        // stage z_f = act(enc_proj[b, t_b + f] + pred_proj[b]), f = 0, 1: all loads of a round are issued before the first use
+        for (int base = 0; base < total; base += kThreads * kJointRound) {
+          float4 e0[kJointRound], e1[kJointRound], q[kJointRound];
 #pragma unroll
-          for (int u = 0; u < kStageRound; ++u) {
+          for (int u = 0; u < kJointRound; ++u) {
             const int idx = base + u * kThreads + tid;
             if (idx < total) {
-              const int bb = s_alist[s0 + idx / J4], k4 = idx % J4;
-              e[u] = __ldg(reinterpret_cast<const float4*>(p.encp + (static_cast<size_t>(bb) * p.T + s_t[bb]) * J) + k4);
+              const int bb = s_alist[s0 + idx / J4], k4 = idx % J4, t0 = s_t[bb], t1 = min(t0 + 1, s_len[bb] - 1);
+              e0[u] = __ldg(reinterpret_cast<const float4*>(p.encp + (static_cast<size_t>(bb) * p.T + t0) * J) + k4);
+              e1[u] = __ldg(reinterpret_cast<const float4*>(p.encp + (static_cast<size_t>(bb) * p.T + t1) * J) + k4);
               q[u] = ldcg4(p.predp + static_cast<size_t>(bb) * J + k4 * 4);
             }
           }
 #pragma unroll
-          for (int u = 0; u < kStageRound; ++u) {
+          for (int u = 0; u < kJointRound; ++u) {
             const int idx = base + u * kThreads + tid;
             if (idx < total) {
+              const int i = idx / J4, k4 = idx % J4;
               float4 z;
-              z.x = act_fn(e[u].x + q[u].x, p.act), z.y = act_fn(e[u].y + q[u].y, p.act);
-              z.z = act_fn(e[u].z + q[u].z, p.act), z.w = act_fn(e[u].w + q[u].w, p.act);
-              s_stage[idx] = z;
+              z.x = act_fn(e0[u].x + q[u].x, p.act), z.y = act_fn(e0[u].y + q[u].y, p.act);
+              z.z = act_fn(e0[u].z + q[u].z, p.act), z.w = act_fn(e0[u].w + q[u].w, p.act);
+              s_stage[(2 * i) * J4 + k4] = z;
+              z.x = act_fn(e1[u].x + q[u].x, p.act), z.y = act_fn(e1[u].y + q[u].y, p.act);
+              z.z = act_fn(e1[u].z + q[u].z, p.act), z.w = act_fn(e1[u].w + q[u].w, p.act);
+              s_stage[(2 * i + 1) * J4 + k4] = z;
             }
           }
         }
         __syncthreads();
         RNNT_TICK(8)
-        const int npairs = (ns + 1) >> 1;
-        for (int task = warp; task < npairs * nchunks; task += kWarps) {
-          const int pr = task % npairs, ch = task / npairs, r0 = ch * 4;
-          const int i0 = 2 * pr, i1 = (2 * pr + 1 < ns) ? 2 * pr + 1 : i0;
-          float acc[4][2] = {};
-          tile_dot(reinterpret_cast<const float4*>(s_wj) + r0 * J4, J4, nj - r0, s_stage + i0 * J4, s_stage + i1 * J4, J4, lane, acc);
-          unsigned long long k0 = 0ull, k1 = 0ull;
+        const int nv = 2 * ns, ngroups = (nv + 3) >> 2;  // staged vector v = 2 * utterance + frame
+        for (int task = warp; task < ngroups * nchunks; task += kWarps) {
+          const int grp = task % ngroups, ch = task / ngroups, r0 = ch * 8;
+          int zi[4];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            if (r0 + r < nj) {
-              const int row = j_lo + r0 + r;
-              const float bias = __ldg(p.b_out + row);
-              const unsigned long long c0 = pack_key(acc[r][0] + bias, row), c1 = pack_key(acc[r][1] + bias, row);
-              k0 = c0 > k0 ? c0 : k0;
-              k1 = c1 > k1 ? c1 : k1;
-            }
+          for (int u = 0; u < 4; ++u) zi[u] = min(4 * grp + u, nv - 1);
+          const float4* wr = reinterpret_cast<const float4*>(s_wj) + r0 * J4;
+          const float total = J4 == 160 ? tile_dot84<5>(wr, J4, nj - r0, s_stage, J4, zi, J4, lane)
+                                        : tile_dot84<0>(wr, J4, nj - r0, s_stage, J4, zi, J4, lane);
+          // lane = row * 4 + vector: bias, key, then the maximum over the 8 rows (lane bits 2..4)
+          const int r = lane >> 2, v = 4 * grp + (lane & 3);
+          unsigned long long key = 0ull;
+          if (r0 + r < nj) key = pack_key(total + __ldg(p.b_out + j_lo + r0 + r), j_lo + r0 + r);
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
           }
-          if (lane == 0) atomicMax(&s_best[s_alist[s0 + i0]], k0);
-          if (lane == 1 && i1 != i0) atomicMax(&s_best[s_alist[s0 + i1]], k1);
+          if (lane < 4 && v < nv) atomicMax(&s_best[(v & 1) * kMaxB + s_alist[s0 + (v >> 1)]], key);
         }
         __syncthreads();
         RNNT_TICK(9)
       }
       __syncthreads();
-      if (nj > 0 && tid < n_active) {
-        const int b = s_alist[tid];
-        atomicMax(&p.slots[(it % 3) * kMaxB + b], s_best[b]);
+      if (nj > 0 && tid < 2 * n_active) {
+        const int b = s_alist[tid >> 1], f = tid & 1;
+        atomicMax(&p.slots[((it % 3) * 2 + f) * kMaxB + b], s_best[f * kMaxB + b]);
       }
       RNNT_TICK(0)
       grid_sync(p.counter, bar_target);
@@ -316,14 +367,18 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
       if (tid < kMaxB) {
         int emit = 0;
         if (tid < B && s_active[tid]) {
-          float v;
-          int k;
-          unpack_key(__ldcg(&p.slots[(it % 3) * kMaxB + tid]), &v, &k);
           int t = s_t[tid], sym = s_sym[tid];
-          if (k == blank) {
-            ++t;
-            sym = 0;
-          } else {
+          const int len = s_len[tid];
+          for (int f = 0; f < 2; ++f) {  // frame t, then (only after a blank) the speculatively evaluated frame t + 1
+            float v;
+            int k;
+            unpack_key(__ldcg(&p.slots[((it % 3) * 2 + f) * kMaxB + tid]), &v, &k);
+            if (k == blank) {
+              ++t;
+              sym = 0;
+              if (t >= len) break;
+              continue;
+            }
             emit = 1;
             const int n = s_ntok[tid];
             if (cta == 0) {
@@ -342,13 +397,17 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
               ++t;
               sym = 0;
             }
+            break;  // the prediction network must advance before the next joint evaluation
           }
           s_t[tid] = t;
           s_sym[tid] = sym;
-          s_active[tid] = t < s_len[tid];
+          s_active[tid] = t < len;
         }
         s_emit[tid] = emit;
-        if (cta == 0) p.slots[((it + 2) % 3) * kMaxB + tid] = 0ull;
+        if (cta == 0) {
+          p.slots[(((it + 2) % 3) * 2 + 0) * kMaxB + tid] = 0ull;
+          p.slots[(((it + 2) % 3) * 2 + 1) * kMaxB + tid] = 0ull;
+        }
       }
       __syncthreads();
       n_emit = build_list(s_emit, B, s_elist, s_tmp);
@@ -391,10 +450,10 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
               const float gi = (lane ? acc[0][1] : acc[0][0]) + bl[0], gf = (lane ? acc[1][1] : acc[1][0]) + bl[1];
               const float gg = (lane ? acc[2][1] : acc[2][0]) + bl[2], go = (lane ? acc[3][1] : acc[3][0]) + bl[3];
               const int par = s_par[b];
-              const float c_old = s_c[(par * kMaxB + b) * p.umax + ul];
+              const float c_old = s_c[(par * B + b) * p.umax + ul];
               const float c_new = sigmoidf_(gf) * c_old + sigmoidf_(gi) * tanhf(gg);
               const float h_new = sigmoidf_(go) * tanhf(c_new);
-              s_c[((par ^ 1) * kMaxB + b) * p.umax + ul] = c_new;
+              s_c[((par ^ 1) * B + b) * p.umax + ul] = c_new;
               p.hbuf[(static_cast<size_t>(par ^ 1) * B + b) * H + u_lo + ul] = h_new;
             }
           }
@@ -461,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
   // ---- results: committed state = the buffer the pending one does not occupy ------------------------------------------------
   for (int i = tid; i < nu * B; i += kThreads) {
     const int ul = i % nu, b = i / nu;
-    p.c_out[static_cast<size_t>(b) * H + u_lo + ul] = s_c[((s_par[b] ^ 1) * kMaxB + b) * p.umax + ul];
+    p.c_out[static_cast<size_t>(b) * H + u_lo + ul] = s_c[((s_par[b] ^ 1) * B + b) * p.umax + ul];
   }
   for (int i = cta * kThreads + tid; i < B * H; i += G * kThreads) {
     const int b = i / H, u = i % H;
@@ -509,7 +568,7 @@ RnntScratch rnnt_scratch_layout(int E, int H, int J, int B, int T) {
   const int Bc = B < kMaxB ? B : kMaxB;
   size_t off = 0;
   s.sync_off = off;
-  s.sync_bytes = align256(512 + sizeof(unsigned long long) * 3 * kMaxB);
+  s.sync_bytes = align256(512 + sizeof(unsigned long long) * 3 * 2 * kMaxB);
   off += s.sync_bytes;
   s.hbuf_off = off;
   s.hbuf_bytes = align256(sizeof(float) * 2 * Bc * H);
@@ -526,12 +585,13 @@ RnntScratch rnnt_scratch_layout(int E, int H, int J, int B, int T) {
   return s;
 }
 
-size_t rnnt_smem_bytes(int H, int J, int V1, int G, int* umax, int* pmax, int* jmax) {
+// dynamic shared memory without the staging buffer
+size_t rnnt_smem_fixed_bytes(int H, int J, int V1, int G, int B, int* umax, int* pmax, int* jmax) {
   *umax = (H + G - 1) / G;
   *pmax = (J + G - 1) / G;
   *jmax = (V1 + G - 1) / G;
   return sizeof(float) * (static_cast<size_t>(*umax) * 4 * 2 * H + static_cast<size_t>(*pmax) * H + static_cast<size_t>(*jmax) * J +
-                          static_cast<size_t>(*umax) * 4 + (static_cast<size_t>(2) * kMaxB * *umax + 3) / 4 * 4 + kStageFloats);
+                          static_cast<size_t>(*umax) * 4 + (static_cast<size_t>(2) * B * *umax + 3) / 4 * 4);
 }
 
 }  // namespace
@@ -572,8 +632,16 @@ int cfb_op_rnnt_greedy(const cfb_rnnt_weights* w, const void* encoded, int x_dty
   RnntParams p = {};
   cudaFuncAttributes fa;
   if (cudaFuncGetAttributes(&fa, rnnt_greedy_kernel) != cudaSuccess) return CFB_ERR_CUDA;
-  const size_t smem = rnnt_smem_bytes(H, J, V1, sms, &p.umax, &p.pmax, &p.jmax);
-  if (smem + fa.sharedSizeBytes > static_cast<size_t>(max_smem)) return CFB_ERR_UNSUPPORTED;  // weights do not fit on chip
+  // shared memory: my weight rows + cell states + as much activation staging as is useful and fits
+  const int Bmax = B < kMaxB ? B : kMaxB;
+  const size_t fixed = rnnt_smem_fixed_bytes(H, J, V1, sms, Bmax, &p.umax, &p.pmax, &p.jmax);
+  const size_t room = static_cast<size_t>(max_smem) > fixed + fa.sharedSizeBytes ? max_smem - fixed - fa.sharedSizeBytes : 0;
+  const size_t useful = sizeof(float) * static_cast<size_t>(Bmax < kMaxTile ? (Bmax + 3) / 4 * 4 : kMaxTile) * (2 * H > J ? 2 * H : J);
+  const size_t need = sizeof(float) * static_cast<size_t>(4) * (2 * H > J ? 2 * H : J);  // one group of 4 utterances
+  if (room < need) return CFB_ERR_UNSUPPORTED;  // weights do not fit on chip
+  const size_t stage = (room < useful ? room : useful) / 16 * 16;
+  p.stage_floats = static_cast<int>(stage / sizeof(float));
+  const size_t smem = fixed + stage;
   if (cudaFuncSetAttribute(rnnt_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
     return CFB_ERR_CUDA;
 

@@ -65,7 +65,7 @@ def main():
     out = greedy.decode_arrays(xg, lg)
     torch.cuda.synchronize()
     n_tok = out["n_tokens"].cpu()
-    phases = dict(zip(["joint", "barrier_joint", "control", "lstm", "barrier_lstm", "pred", "barrier_pred", "loop", "joint_stage", "joint_compute"],
+    phases = dict(zip(["joint", "barrier_joint", "control", "lstm", "barrier_lstm", "pred", "barrier_pred", "loop", "joint_stage", "joint_compute", "iterations"],
                       out["phase_cycles"].cpu().tolist()))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(args.warmup):
@@ -82,7 +82,7 @@ def main():
         greedy(encoder_output=xg, encoded_lengths=lg)
     e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
     audio_s = B * T * 0.04  # 40 ms per encoder frame (10 ms hop x 4 subsampling)
-    iters = int((T + n_tok).max())  # lock-step iterations = frames + symbols of the slowest utterance
+    iters = int(phases.pop("iterations"))  # lock-step iterations (each consumes up to two frames or one symbol per utterance)
     line = dict(metric="transducer greedy decode audio-sec/sec", value=audio_s / (ms * 1e-3), unit="audio-sec/sec",
                 ms_per_batch=ms, e2e=dict(value=audio_s / (e2e_ms * 1e-3), ms_per_batch=e2e_ms,
                                           mode="GreedyBatchedRNNTInfer.forward: decode + hypotheses on the host"),
