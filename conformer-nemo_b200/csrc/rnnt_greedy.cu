@@ -141,20 +141,22 @@ __device__ __forceinline__ void tile_dot(const float4* __restrict__ w, int row_s
   }
 }
 
-// 8 weight rows x 4 staged activation vectors: acc[r * 4 + s] += sum_k w[r][k] * z_s[k] over this lane's k, then a transposing
-// butterfly (31 shuffles instead of 160) leaves the warp total of accumulator i in lane i: lane = row * 4 + utterance.
-template <int NI>
-__device__ __forceinline__ float tile_dot84(const float4* __restrict__ w, int row_stride4, int nrows, const float4* __restrict__ z,
-                                            int z_stride4, const int zi[4], int K4, int lane) {
-  float acc[32];
+// R (4 or 8) weight rows x 4 staged activation vectors: acc[r * 4 + s] += sum_k w[r][k] * z_s[k] over this lane's k, then a
+// transposing butterfly (R * 4 - 1 shuffles instead of R * 20) leaves the warp total of accumulator i in lane i (and in
+// lane i + 16 when R == 4): lane = row * 4 + vector.
+template <int R, int NI>
+__device__ __forceinline__ float tile_dot_r4(const float4* __restrict__ w, int row_stride4, int nrows, const float4* __restrict__ z,
+                                             int z_stride4, const int zi[4], int K4, int lane) {
+  constexpr int NV = R * 4;
+  float acc[NV];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  for (int i = 0; i < NV; ++i) acc[i] = 0.f;
   auto step = [&](int k4) {
     float4 a[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) a[s] = z[zi[s] * z_stride4 + k4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < R; ++r) {
       const float4 v = w[(r < nrows ? r : 0) * row_stride4 + k4];
 #pragma unroll
       for (int s = 0; s < 4; ++s) acc[r * 4 + s] = dot4(v, a[s], acc[r * 4 + s]);
@@ -167,7 +169,7 @@ __device__ __forceinline__ float tile_dot84(const float4* __restrict__ w, int ro
     for (int k4 = lane; k4 < K4; k4 += 32) step(k4);
   }
 #pragma unroll
-  for (int half = 16; half > 0; half >>= 1) {
+  for (int half = NV / 2; half > 0; half >>= 1) {
     const bool up = (lane & half) != 0;
 #pragma unroll
     for (int i = 0; i < half; ++i) {
@@ -176,6 +178,8 @@ __device__ __forceinline__ float tile_dot84(const float4* __restrict__ w, int ro
       acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
     }
   }
+#pragma unroll
+  for (int o = NV; o < 32; o <<= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
   return acc[0];
 }
 
@@ -338,8 +342,8 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
 #pragma unroll
           for (int u = 0; u < 4; ++u) zi[u] = min(4 * grp + u, nv - 1);
           const float4* wr = reinterpret_cast<const float4*>(s_wj) + r0 * J4;
-          const float total = J4 == 160 ? tile_dot84<5>(wr, J4, nj - r0, s_stage, J4, zi, J4, lane)
-                                        : tile_dot84<0>(wr, J4, nj - r0, s_stage, J4, zi, J4, lane);
+          const float total = J4 == 160 ? tile_dot_r4<8, 5>(wr, J4, nj - r0, s_stage, J4, zi, J4, lane)
+                                        : tile_dot_r4<8, 0>(wr, J4, nj - r0, s_stage, J4, zi, J4, lane);
           // lane = row * 4 + vector: bias, key, then the maximum over the 8 rows (lane bits 2..4)
           const int r = lane >> 2, v = 4 * grp + (lane & 3);
           unsigned long long key = 0ull;
@@ -437,18 +441,22 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
             }
           }
           __syncthreads();
-          const int npe = (ns + 1) >> 1;
-          for (int task = warp; task < npe * nu; task += kWarps) {
-            const int pr = task % npe, ul = task / npe;
-            const int i0 = 2 * pr, i1 = (2 * pr + 1 < ns) ? 2 * pr + 1 : i0;
-            float acc[4][2] = {};
-            tile_dot(reinterpret_cast<const float4*>(s_wl) + static_cast<size_t>(ul) * 4 * K24, K24, 4, s_stage + i0 * K24,
-                     s_stage + i1 * K24, K24, lane, acc);
-            if (lane < 2 && (lane == 0 || i1 != i0)) {
-              const int b = s_elist[s0 + (lane == 0 ? i0 : i1)];
-              const float* bl = s_bl + ul * 4;
-              const float gi = (lane ? acc[0][1] : acc[0][0]) + bl[0], gf = (lane ? acc[1][1] : acc[1][0]) + bl[1];
-              const float gg = (lane ? acc[2][1] : acc[2][0]) + bl[2], go = (lane ? acc[3][1] : acc[3][0]) + bl[3];
+          const int ngr = (ns + 3) >> 2;  // tasks = (hidden unit: its 4 gate rows) x (group of 4 utterances)
+          for (int task = warp; task < ngr * nu; task += kWarps) {
+            const int grp = task % ngr, ul = task / ngr;
+            int zi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) zi[u] = min(4 * grp + u, ns - 1);
+            const float4* wr = reinterpret_cast<const float4*>(s_wl) + static_cast<size_t>(ul) * 4 * K24;
+            const float total = K24 == 320 ? tile_dot_r4<4, 10>(wr, K24, 4, s_stage, K24, zi, K24, lane)
+                                           : tile_dot_r4<4, 0>(wr, K24, 4, s_stage, K24, zi, K24, lane);
+            // lane = gate * 4 + utterance: hand the four gate pre-activations of utterance u to lane u
+            const int u = lane & 3;
+            const float* bl = s_bl + ul * 4;
+            const float gi = __shfl_sync(0xffffffffu, total, u) + bl[0], gf = __shfl_sync(0xffffffffu, total, 4 + u) + bl[1];
+            const float gg = __shfl_sync(0xffffffffu, total, 8 + u) + bl[2], go = __shfl_sync(0xffffffffu, total, 12 + u) + bl[3];
+            if (lane < 4 && 4 * grp + u < ns) {
+              const int b = s_elist[s0 + 4 * grp + u];
               const int par = s_par[b];
               const float c_old = s_c[(par * B + b) * p.umax + ul];
               const float c_new = sigmoidf_(gf) * c_old + sigmoidf_(gi) * tanhf(gg);
