@@ -190,7 +190,7 @@ def test_gpu_bf16_encoder_output_and_token_buffer_growth():
 @pytest.mark.gpu
 def test_gpu_full_size_properties():
     """BASELINE cfg 3 sizes (transducer-large decoder on 32 x T' = 500 frames): decoding an utterance alone, in another
-    batch order or in a batch of more than 256 utterances (two launches) gives bit-identical hypotheses; lengths bound
+    batch order or in a batch of more than 128 utterances (several launches) gives bit-identical hypotheses; lengths bound
     the timesteps; at most max_symbols per frame."""
     dims = (512, 640, 640, 1024)
     dec_sd, joint_sd = ro.random_rnnt_state_dicts(*dims, seed=41, blank_bias=1.2)
@@ -216,7 +216,7 @@ def test_gpu_full_size_properties():
     # oracle on a sample of utterances at the full sizes
     want = ro.rnnt_greedy_decode(x[:3], lens[:3], dec_sd, joint_sd, 30, "relu", False)
     assert _compare(hyps[:3], want) == []
-    # > 256 utterances: the host entry point splits the batch into launches of 256
+    # > 128 utterances: the host entry point splits the batch into launches of 128
     reps = 9
     big = _decode_gpu(greedy, x[:, :, :60].repeat(reps, 1, 1), torch.clamp(lens, max=60).repeat(reps))
     for i in range(B, reps * B):
