@@ -16,6 +16,7 @@
 //     atomicMax (value bits | inverted index => first index wins ties like torch.max),
 //   * phases are separated by a grid barrier (1 per blank-only iteration, 3 when something was emitted).
 #include <float.h>
+#include <stdlib.h>
 
 #include "../../include/cfb.h"
 #include "common.cuh"
@@ -165,6 +166,10 @@ __device__ __forceinline__ float tile_dot_r4(const float4* __restrict__ w, int r
   if (NI > 0) {
 #pragma unroll
     for (int i = 0; i < NI; ++i) step(lane + 32 * i);
+  } else if (NI < 0) {  // -NI unrolled iterations, the last one partial (K4 not a multiple of 32)
+#pragma unroll
+    for (int i = 0; i < -NI; ++i)
+      if (lane + 32 * i < K4) step(lane + 32 * i);
   } else {
     for (int k4 = lane; k4 < K4; k4 += 32) step(k4);
   }
@@ -540,6 +545,399 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
   }
 }
 
+// ======================================================================================================================
+// Cluster variant: the same decode with the weights split over rows ACROSS clusters of 4 CTAs and over K INSIDE a cluster.
+// Cluster q owns a block of hidden units / joint.pred rows / output rows; rank r of the cluster keeps the K-quarter r of all
+// of them, so a CTA stages only a quarter of every activation vector (the per-SM ingest from L2 was the limit of the
+// row-only partition: every CTA read every utterance's vectors).  The four partial dot products of a row meet in the shared
+// memory of the row's owner rank (st.shared::cluster) and are added there in rank order 0..3 -- a fixed order, so results
+// do not depend on the batch or on timing.  One cluster barrier per tile; partial buffers are double-buffered, which is
+// enough because a rank cannot pass barrier n + 1 before every rank has finished reading the partials of barrier n.
+constexpr int kC = 4;            // CTAs per cluster
+constexpr int kTileL = 16;       // utterances per LSTM tile
+constexpr int kTileP = 32;       // utterances per joint.pred tile
+constexpr int kTileV = 64;       // staged vectors per joint tile (32 utterances x 2 frames)
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* ptr) { return static_cast<uint32_t>(__cvta_generic_to_shared(ptr)); }
+__device__ __forceinline__ void st_cluster_f32(const float* local_ptr, int rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr_u32(local_ptr)), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// owner rank of element i when n elements are split with row_range over kC ranks, and its index inside the owner's slice
+__device__ __forceinline__ void owner_of(int i, int n, int* rank, int* local) {
+  int o = 0, lo = 0;
+#pragma unroll
+  for (int c = 0; c < kC; ++c) {
+    const int l = n * c / kC, h = n * (c + 1) / kC;
+    if (i >= l && i < h) {
+      o = c;
+      lo = l;
+    }
+  }
+  *rank = o;
+  *local = i - lo;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_c4_kernel(const RnntParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, cta = blockIdx.x, NQ = G / kC, q = cta / kC, r = cta % kC;
+  const int H = p.H, J = p.J, V1 = p.V1, B = p.B;
+  const int blank = V1 - 1;
+  const int Lq = H / 2, Hq = H / 4, Jq = J / 4;          // K slices (floats): LSTM [x | h], joint.pred, output layer
+  const int Lq4 = Lq / 4, Hq4 = Hq / 4, Jq4 = Jq / 4;
+
+  int uq_lo, uq_hi, pq_lo, pq_hi, jq_lo, jq_hi;          // the cluster's rows
+  row_range(H, q, NQ, &uq_lo, &uq_hi);
+  row_range(J, q, NQ, &pq_lo, &pq_hi);
+  row_range(V1, q, NQ, &jq_lo, &jq_hi);
+  const int nuq = uq_hi - uq_lo, npq = pq_hi - pq_lo, njq = jq_hi - jq_lo;
+  int mu_lo, mu_hi, mp_lo, mp_hi;                        // the rows this rank finalises (relative to the cluster's)
+  row_range(nuq, r, kC, &mu_lo, &mu_hi);
+  row_range(npq, r, kC, &mp_lo, &mp_hi);
+  const int nmu = mu_hi - mu_lo, nmp = mp_hi - mp_lo;
+  const int nchunks = (njq + 7) >> 3;                    // output rows in chunks of 8; chunk c is finalised by rank c (host: <= kC)
+  const int mumax = (p.umax + kC - 1) / kC, mpmax = (p.pmax + kC - 1) / kC;
+
+  float* s_wl = smem;                                               // [umax][4][Lq]
+  float* s_wp = s_wl + static_cast<size_t>(p.umax) * 4 * Lq;        // [pmax][Hq]
+  float* s_wj = s_wp + static_cast<size_t>(p.pmax) * Hq;            // [jmax][Jq]
+  float* s_bl = s_wj + static_cast<size_t>(p.jmax) * Jq;            // [mumax][4]
+  float* s_c = s_bl + mumax * 4;                                    // [2][B][mumax]
+  float* s_pj = s_c + ((static_cast<size_t>(2) * B * mumax + 3) / 4) * 4;  // [2][kC][8][kTileV]   partial logits
+  float* s_pl = s_pj + 2 * kC * 8 * kTileV;                         // [2][kC][mumax][4][kTileL] partial gates
+  float* s_pp = s_pl + 2 * kC * mumax * 4 * kTileL;                 // [2][kC][mpmax][kTileP]    partial joint.pred
+  float4* s_stage = reinterpret_cast<float4*>(s_pp + ((2 * kC * mpmax * kTileP + 3) / 4) * 4);
+  const int tile_s = min(kTileV / 2, p.stage_floats / (2 * Jq)) & ~1;   // utterances per joint tile (two vectors each)
+  const int tile_l = min(kTileL, p.stage_floats / Lq) & ~3, tile_p = min(kTileP, p.stage_floats / Hq) & ~3;
+  __shared__ unsigned long long s_best[2 * kMaxB];
+  __shared__ double s_score[kMaxB];
+  __shared__ int s_t[kMaxB], s_sym[kMaxB], s_last[kMaxB], s_par[kMaxB], s_ntok[kMaxB], s_len[kMaxB];
+  __shared__ int s_active[kMaxB], s_emit[kMaxB], s_alist[kMaxB], s_elist[kMaxB];
+  __shared__ int s_tmp[kWarps];
+
+  // ---- my K-quarter of the cluster's weight rows (once) --------------------------------------------------------------------
+  for (int i = tid; i < nuq * 4 * Lq4; i += kThreads) {
+    const int k4 = i % Lq4, rr = i / Lq4, gate = rr & 3, ul = rr >> 2;
+    const int row = gate * H + uq_lo + ul;
+    const float* src = r < 2 ? p.w_ih + static_cast<size_t>(row) * H + r * Lq + k4 * 4
+                             : p.w_hh + static_cast<size_t>(row) * H + (r - 2) * Lq + k4 * 4;
+    reinterpret_cast<float4*>(s_wl)[i] = __ldg(reinterpret_cast<const float4*>(src));
+  }
+  for (int i = tid; i < npq * Hq4; i += kThreads)
+    reinterpret_cast<float4*>(s_wp)[i] =
+        __ldg(reinterpret_cast<const float4*>(p.w_pred + static_cast<size_t>(pq_lo + i / Hq4) * H + r * Hq) + i % Hq4);
+  for (int i = tid; i < njq * Jq4; i += kThreads)
+    reinterpret_cast<float4*>(s_wj)[i] =
+        __ldg(reinterpret_cast<const float4*>(p.w_out + static_cast<size_t>(jq_lo + i / Jq4) * J + r * Jq) + i % Jq4);
+  for (int i = tid; i < nmu * 4; i += kThreads) {
+    const int row = (i & 3) * H + uq_lo + mu_lo + (i >> 2);
+    s_bl[i] = p.b_ih[row] + p.b_hh[row];
+  }
+  if (tid < kMaxB) {
+    const int len = tid < B ? min(max(p.lens[tid], 0), p.T) : 0;
+    s_len[tid] = len;
+    s_t[tid] = 0;
+    s_sym[tid] = 0;
+    s_last[tid] = blank;
+    s_par[tid] = 0;
+    s_ntok[tid] = 0;
+    s_score[tid] = 0.0;
+    s_active[tid] = len > 0;
+    s_emit[tid] = tid < B;
+  }
+  __syncthreads();
+  // SOS: pending = LSTM(0; 0, 0) = f(bias) for the units this rank finalises; committed state = 0 (hbuf[1] is zeroed)
+  for (int i = tid; i < nmu * B; i += kThreads) {
+    const int m = i % nmu, b = i / nmu;
+    const float* bl = s_bl + m * 4;
+    const float c1 = sigmoidf_(bl[0]) * tanhf(bl[2]);
+    const float h1 = sigmoidf_(bl[3]) * tanhf(c1);
+    s_c[(0 * B + b) * mumax + m] = c1;
+    s_c[(1 * B + b) * mumax + m] = 0.f;
+    p.hbuf[(static_cast<size_t>(0) * B + b) * H + uq_lo + mu_lo + m] = h1;
+  }
+  unsigned int bar_target = 0;
+  int jbuf = 0, lbuf = 0, pbuf = 0;
+  int n_emit = build_list(s_emit, B, s_elist, s_tmp);
+  int n_active = build_list(s_active, B, s_alist, s_tmp);
+  cluster_sync_all();  // every CTA of the cluster is running before the first remote shared-memory store
+  grid_sync(p.counter, bar_target);
+
+  bool first = true;
+  unsigned long long* timers = reinterpret_cast<unsigned long long*>(p.counter + 16);
+  long long tk = clock64();
+  for (unsigned int it = 0;; ++it) {
+    if (!first) {
+      RNNT_TICK(7)
+      if (cta == 0 && tid == 0) timers[10] += 1;
+      // ---- joint at frames t and t + 1 of every active utterance ----------------------------------------------------------------
+      if (tid < 2 * kMaxB) s_best[tid] = 0ull;
+      __syncthreads();
+      for (int s0 = 0; s0 < n_active; s0 += tile_s) {
+        const int ns = min(tile_s, n_active - s0), total = ns * Jq4;
+        for (int base = 0; base < total; base += kThreads * kJointRound) {
+          float4 e0[kJointRound], e1[kJointRound], qq[kJointRound];
+#pragma unroll
+          for (int u = 0; u < kJointRound; ++u) {
+            const int idx = base + u * kThreads + tid;
+            if (idx < total) {
+              const int bb = s_alist[s0 + idx / Jq4], k4 = idx % Jq4, t0 = s_t[bb], t1 = min(t0 + 1, s_len[bb] - 1);
+              e0[u] = __ldg(reinterpret_cast<const float4*>(p.encp + (static_cast<size_t>(bb) * p.T + t0) * J + r * Jq) + k4);
+              e1[u] = __ldg(reinterpret_cast<const float4*>(p.encp + (static_cast<size_t>(bb) * p.T + t1) * J + r * Jq) + k4);
+              qq[u] = ldcg4(p.predp + static_cast<size_t>(bb) * J + r * Jq + k4 * 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kJointRound; ++u) {
+            const int idx = base + u * kThreads + tid;
+            if (idx < total) {
+              const int i = idx / Jq4, k4 = idx % Jq4;
+              float4 z;
+              z.x = act_fn(e0[u].x + qq[u].x, p.act), z.y = act_fn(e0[u].y + qq[u].y, p.act);
+              z.z = act_fn(e0[u].z + qq[u].z, p.act), z.w = act_fn(e0[u].w + qq[u].w, p.act);
+              s_stage[(2 * i) * Jq4 + k4] = z;
+              z.x = act_fn(e1[u].x + qq[u].x, p.act), z.y = act_fn(e1[u].y + qq[u].y, p.act);
+              z.z = act_fn(e1[u].z + qq[u].z, p.act), z.w = act_fn(e1[u].w + qq[u].w, p.act);
+              s_stage[(2 * i + 1) * Jq4 + k4] = z;
+            }
+          }
+        }
+        __syncthreads();
+        RNNT_TICK(8)
+        const int nv = 2 * ns, ngroups = (nv + 3) >> 2;
+        float* pj = s_pj + jbuf * (kC * 8 * kTileV);
+        for (int task = warp; task < ngroups * nchunks; task += kWarps) {
+          const int grp = task % ngroups, ch = task / ngroups;
+          int zi[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) zi[u] = min(4 * grp + u, nv - 1);
+          const float4* wr = reinterpret_cast<const float4*>(s_wj) + ch * 8 * Jq4;
+          const float total_k = Jq4 == 40 ? tile_dot_r4<8, -2>(wr, Jq4, njq - ch * 8, s_stage, Jq4, zi, Jq4, lane)
+                                          : tile_dot_r4<8, 0>(wr, Jq4, njq - ch * 8, s_stage, Jq4, zi, Jq4, lane);
+          const int row = lane >> 2, v = 4 * grp + (lane & 3);  // partial logit of (row, vector) -> the chunk's owner rank
+          if (v < nv) st_cluster_f32(pj + (r * 8 + row) * kTileV + v, ch, total_k);
+        }
+        cluster_sync_all();
+        if (r < nchunks && tid < 8 * kTileV) {
+          const int row = tid / kTileV, v = tid % kTileV;
+          if (v < nv && r * 8 + row < njq) {
+            const float* src = pj + row * kTileV + v;
+            const float sum = ((src[0] + src[8 * kTileV]) + src[2 * 8 * kTileV]) + src[3 * 8 * kTileV];
+            const int out_row = jq_lo + r * 8 + row;
+            atomicMax(&s_best[(v & 1) * kMaxB + s_alist[s0 + (v >> 1)]], pack_key(sum + __ldg(p.b_out + out_row), out_row));
+          }
+        }
+        jbuf ^= 1;
+        __syncthreads();
+        RNNT_TICK(9)
+      }
+      if (r < nchunks && tid < 2 * n_active) {
+        const int b = s_alist[tid >> 1], f = tid & 1;
+        atomicMax(&p.slots[((it % 3) * 2 + f) * kMaxB + b], s_best[f * kMaxB + b]);
+      }
+      RNNT_TICK(0)
+      grid_sync(p.counter, bar_target);
+      RNNT_TICK(1)
+
+      // ---- control update (replicated in every CTA) ---------------------------------------------------------------------------
+      if (tid < kMaxB) {
+        int emit = 0;
+        if (tid < B && s_active[tid]) {
+          int t = s_t[tid], sym = s_sym[tid];
+          const int len = s_len[tid];
+          for (int f = 0; f < 2; ++f) {
+            float v;
+            int k;
+            unpack_key(__ldcg(&p.slots[((it % 3) * 2 + f) * kMaxB + tid]), &v, &k);
+            if (k == blank) {
+              ++t;
+              sym = 0;
+              if (t >= len) break;
+              continue;
+            }
+            emit = 1;
+            const int n = s_ntok[tid];
+            if (cta == 0) {
+              if (n < p.max_tokens) {
+                p.tokens[static_cast<size_t>(tid) * p.max_tokens + n] = k;
+                p.timesteps[static_cast<size_t>(tid) * p.max_tokens + n] = t;
+              } else {
+                atomicOr(p.flags, 1);
+              }
+              s_score[tid] += static_cast<double>(v);
+            }
+            s_ntok[tid] = n + 1;
+            s_last[tid] = k;
+            if (++sym >= (p.max_symbols > 0 ? p.max_symbols : kHardSymbolLimit)) {
+              if (p.max_symbols <= 0 && cta == 0) atomicOr(p.flags, 2);
+              ++t;
+              sym = 0;
+            }
+            break;
+          }
+          s_t[tid] = t;
+          s_sym[tid] = sym;
+          s_active[tid] = t < len;
+        }
+        s_emit[tid] = emit;
+        if (cta == 0) {
+          p.slots[(((it + 2) % 3) * 2 + 0) * kMaxB + tid] = 0ull;
+          p.slots[(((it + 2) % 3) * 2 + 1) * kMaxB + tid] = 0ull;
+        }
+      }
+      __syncthreads();
+      n_emit = build_list(s_emit, B, s_elist, s_tmp);
+      n_active = build_list(s_active, B, s_alist, s_tmp);
+      RNNT_TICK(2)
+
+      // ---- LSTM cell for the utterances that emitted ---------------------------------------------------------------------------
+      if (n_emit > 0) {
+        for (int s0 = 0; s0 < n_emit; s0 += tile_l) {
+          const int ns = min(tile_l, n_emit - s0), total = ns * Lq4;
+          for (int base = 0; base < total; base += kThreads * kStageRound) {
+            float4 v[kStageRound];
+#pragma unroll
+            for (int u = 0; u < kStageRound; ++u) {
+              const int idx = base + u * kThreads + tid;
+              if (idx < total) {
+                const int bb = s_elist[s0 + idx / Lq4], k4 = idx % Lq4;
+                v[u] = r < 2 ? __ldg(reinterpret_cast<const float4*>(p.embed + static_cast<size_t>(s_last[bb]) * H + r * Lq) + k4)
+                             : ldcg4(p.hbuf + (static_cast<size_t>(s_par[bb]) * B + bb) * H + (r - 2) * Lq + k4 * 4);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < kStageRound; ++u) {
+              const int idx = base + u * kThreads + tid;
+              if (idx < total) s_stage[idx] = v[u];
+            }
+          }
+          __syncthreads();
+          const int ngr = (ns + 3) >> 2;
+          float* pl = s_pl + lbuf * (kC * mumax * 4 * kTileL);
+          for (int task = warp; task < ngr * nuq; task += kWarps) {
+            const int grp = task % ngr, ul = task / ngr;
+            int zi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) zi[u] = min(4 * grp + u, ns - 1);
+            const float4* wr = reinterpret_cast<const float4*>(s_wl) + static_cast<size_t>(ul) * 4 * Lq4;
+            const float total_k = Lq4 == 80 ? tile_dot_r4<4, -3>(wr, Lq4, 4, s_stage, Lq4, zi, Lq4, lane)
+                                            : tile_dot_r4<4, 0>(wr, Lq4, 4, s_stage, Lq4, zi, Lq4, lane);
+            int owner, m;
+            owner_of(ul, nuq, &owner, &m);
+            const int gate = (lane >> 2) & 3, sidx = 4 * grp + (lane & 3);
+            if (lane < 16 && sidx < ns) st_cluster_f32(pl + ((r * mumax + m) * 4 + gate) * kTileL + sidx, owner, total_k);
+          }
+          cluster_sync_all();
+          if (tid < nmu * kTileL) {
+            const int m = tid / kTileL, sidx = tid % kTileL;
+            if (sidx < ns) {
+              float g4[4];
+#pragma unroll
+              for (int gate = 0; gate < 4; ++gate) {
+                const float* src = pl + (m * 4 + gate) * kTileL + sidx;
+                const int st = mumax * 4 * kTileL;
+                g4[gate] = (((src[0] + src[st]) + src[2 * st]) + src[3 * st]) + s_bl[m * 4 + gate];
+              }
+              const int b = s_elist[s0 + sidx];
+              const int par = s_par[b];
+              const float c_old = s_c[(par * B + b) * mumax + m];
+              const float c_new = sigmoidf_(g4[1]) * c_old + sigmoidf_(g4[0]) * tanhf(g4[2]);
+              const float h_new = sigmoidf_(g4[3]) * tanhf(c_new);
+              s_c[((par ^ 1) * B + b) * mumax + m] = c_new;
+              p.hbuf[(static_cast<size_t>(par ^ 1) * B + b) * H + uq_lo + mu_lo + m] = h_new;
+            }
+          }
+          lbuf ^= 1;
+          __syncthreads();
+        }
+        if (tid < n_emit) s_par[s_elist[tid]] ^= 1;
+        RNNT_TICK(3)
+        grid_sync(p.counter, bar_target);
+        RNNT_TICK(4)
+      }
+      if (n_active == 0) break;
+    }
+    first = false;
+
+    // ---- joint.pred of the new prediction-network outputs ---------------------------------------------------------------------
+    if (n_emit > 0) {
+      const int nch4 = (npq + 3) >> 2;
+      for (int s0 = 0; s0 < n_emit; s0 += tile_p) {
+        const int ns = min(tile_p, n_emit - s0), total = ns * Hq4;
+        for (int base = 0; base < total; base += kThreads * kStageRound) {
+          float4 v[kStageRound];
+#pragma unroll
+          for (int u = 0; u < kStageRound; ++u) {
+            const int idx = base + u * kThreads + tid;
+            if (idx < total) {
+              const int bb = s_elist[s0 + idx / Hq4];
+              v[u] = ldcg4(p.hbuf + (static_cast<size_t>(s_par[bb]) * B + bb) * H + r * Hq + (idx % Hq4) * 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kStageRound; ++u) {
+            const int idx = base + u * kThreads + tid;
+            if (idx < total) s_stage[idx] = v[u];
+          }
+        }
+        __syncthreads();
+        const int ngr = (ns + 3) >> 2;
+        float* pp = s_pp + pbuf * (kC * mpmax * kTileP);
+        for (int task = warp; task < ngr * nch4; task += kWarps) {
+          const int grp = task % ngr, ch = task / ngr;
+          int zi[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) zi[u] = min(4 * grp + u, ns - 1);
+          const float4* wr = reinterpret_cast<const float4*>(s_wp) + ch * 4 * Hq4;
+          const float total_k = Hq4 == 40 ? tile_dot_r4<4, -2>(wr, Hq4, npq - ch * 4, s_stage, Hq4, zi, Hq4, lane)
+                                          : tile_dot_r4<4, 0>(wr, Hq4, npq - ch * 4, s_stage, Hq4, zi, Hq4, lane);
+          const int row = ch * 4 + ((lane >> 2) & 3), sidx = 4 * grp + (lane & 3);
+          if (lane < 16 && row < npq && sidx < ns) {
+            int owner, m;
+            owner_of(row, npq, &owner, &m);
+            st_cluster_f32(pp + (r * mpmax + m) * kTileP + sidx, owner, total_k);
+          }
+        }
+        cluster_sync_all();
+        if (tid < nmp * kTileP) {
+          const int m = tid / kTileP, sidx = tid % kTileP;
+          if (sidx < ns) {
+            const float* src = pp + m * kTileP + sidx;
+            const int st = mpmax * kTileP, row = pq_lo + mp_lo + m;
+            p.predp[static_cast<size_t>(s_elist[s0 + sidx]) * J + row] =
+                (((src[0] + src[st]) + src[2 * st]) + src[3 * st]) + __ldg(p.b_pred + row);
+          }
+        }
+        pbuf ^= 1;
+        __syncthreads();
+      }
+      RNNT_TICK(5)
+      grid_sync(p.counter, bar_target);
+      RNNT_TICK(6)
+    }
+    if (n_active == 0) break;
+  }
+
+  for (int i = tid; i < nmu * B; i += kThreads) {
+    const int m = i % nmu, b = i / nmu;
+    p.c_out[static_cast<size_t>(b) * H + uq_lo + mu_lo + m] = s_c[((s_par[b] ^ 1) * B + b) * mumax + m];
+  }
+  for (int i = cta * kThreads + tid; i < B * H; i += G * kThreads) {
+    const int b = i / H, u = i % H;
+    p.h_out[i] = __ldcg(p.hbuf + (static_cast<size_t>(s_par[b] ^ 1) * B + b) * H + u);
+  }
+  if (cta == 0 && tid < B) {
+    p.n_tokens[tid] = s_ntok[tid];
+    p.scores[tid] = static_cast<float>(s_score[tid]);
+  }
+  cluster_sync_all();  // no CTA of the cluster exits while a sibling could still address its shared memory
+}
+
 // fp32 (rows, K) -> bf16 (rows, 3K) [hi | hi | lo]   (mode 0, activations)
 //                -> bf16 (rows, 3K) [hi | lo | hi]   (mode 1, weights)
 // bf16 input (mode 2): (rows, K) -> (rows, 2K) [x | x]
@@ -602,6 +1000,61 @@ size_t rnnt_smem_fixed_bytes(int H, int J, int V1, int G, int B, int* umax, int*
                           static_cast<size_t>(*umax) * 4 + (static_cast<size_t>(2) * B * *umax + 3) / 4 * 4);
 }
 
+// cluster variant: dynamic shared memory without the staging buffer (rows per CLUSTER in umax / pmax / jmax)
+size_t rnnt_c4_fixed_bytes(int H, int J, int V1, int NQ, int B, int* umax, int* pmax, int* jmax) {
+  *umax = (H + NQ - 1) / NQ;
+  *pmax = (J + NQ - 1) / NQ;
+  *jmax = (V1 + NQ - 1) / NQ;
+  const size_t mumax = (*umax + kC - 1) / kC, mpmax = (*pmax + kC - 1) / kC;
+  return sizeof(float) * (static_cast<size_t>(*umax) * 4 * (H / 2) + static_cast<size_t>(*pmax) * (H / 4) +
+                          static_cast<size_t>(*jmax) * (J / 4) + mumax * 4 + (static_cast<size_t>(2) * B * mumax + 3) / 4 * 4 +
+                          static_cast<size_t>(2) * kC * 8 * kTileV + static_cast<size_t>(2) * kC * mumax * 4 * kTileL +
+                          (static_cast<size_t>(2) * kC * mpmax * kTileP + 3) / 4 * 4);
+}
+
+// Plans the cluster variant: number of co-resident clusters, shared-memory split.  Returns false when it is not asked for
+// or the device / the sizes rule it out (the row-partitioned kernel is used then).
+bool rnnt_c4_plan(int H, int J, int V1, int Bmax, int max_smem, RnntParams* p, int* grid, size_t* smem) {
+  // opt-in (CFB_RNNT_CLUSTER=1): measured 12.6 ms against 13.5 ms for 32 x 500 frames, but the four-fold number of smaller
+  // dot-product tiles costs what the smaller ingest saves once the batch grows
+  const char* env = getenv("CFB_RNNT_CLUSTER");
+  if (env == nullptr || atoi(env) == 0 || (H % 16) || (J % 16)) return false;
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, rnnt_greedy_c4_kernel) != cudaSuccess) return false;
+  const size_t budget = static_cast<size_t>(max_smem) - fa.sharedSizeBytes;
+  if (cudaFuncSetAttribute(rnnt_greedy_c4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)) != cudaSuccess)
+    return false;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kC * 64);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = budget;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int nq = 0;
+  if (cudaOccupancyMaxActiveClusters(&nq, rnnt_greedy_c4_kernel, &cfg) != cudaSuccess || nq < 8) {
+    cudaGetLastError();
+    return false;
+  }
+  const size_t fixed = rnnt_c4_fixed_bytes(H, J, V1, nq, Bmax, &p->umax, &p->pmax, &p->jmax);
+  if ((p->jmax + 7) / 8 > kC) return false;  // more 8-row output chunks per cluster than ranks to finalise them
+  const size_t need = sizeof(float) * static_cast<size_t>(4) * (H / 2 > 2 * (J / 4) ? H / 2 : 2 * (J / 4));
+  if (budget < fixed + need) return false;
+  size_t useful = static_cast<size_t>(kTileV) * (J / 4);
+  if (static_cast<size_t>(kTileL) * (H / 2) > useful) useful = static_cast<size_t>(kTileL) * (H / 2);
+  if (static_cast<size_t>(kTileP) * (H / 4) > useful) useful = static_cast<size_t>(kTileP) * (H / 4);
+  useful *= sizeof(float);
+  const size_t stage = (budget - fixed < useful ? budget - fixed : useful) / 16 * 16;
+  p->stage_floats = static_cast<int>(stage / sizeof(float));
+  *grid = nq * kC;
+  *smem = fixed + stage;
+  return true;
+}
+
 }  // namespace
 }  // namespace cfb
 
@@ -642,16 +1095,22 @@ int cfb_op_rnnt_greedy(const cfb_rnnt_weights* w, const void* encoded, int x_dty
   if (cudaFuncGetAttributes(&fa, rnnt_greedy_kernel) != cudaSuccess) return CFB_ERR_CUDA;
   // shared memory: my weight rows + cell states + as much activation staging as is useful and fits
   const int Bmax = B < kMaxB ? B : kMaxB;
-  const size_t fixed = rnnt_smem_fixed_bytes(H, J, V1, sms, Bmax, &p.umax, &p.pmax, &p.jmax);
-  const size_t room = static_cast<size_t>(max_smem) > fixed + fa.sharedSizeBytes ? max_smem - fixed - fa.sharedSizeBytes : 0;
-  const size_t useful = sizeof(float) * static_cast<size_t>(Bmax < kMaxTile ? (Bmax + 3) / 4 * 4 : kMaxTile) * (2 * H > J ? 2 * H : J);
-  const size_t need = sizeof(float) * static_cast<size_t>(4) * (2 * H > J ? 2 * H : J);  // one group of 4 utterances
-  if (room < need) return CFB_ERR_UNSUPPORTED;  // weights do not fit on chip
-  const size_t stage = (room < useful ? room : useful) / 16 * 16;
-  p.stage_floats = static_cast<int>(stage / sizeof(float));
-  const size_t smem = fixed + stage;
-  if (cudaFuncSetAttribute(rnnt_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
-    return CFB_ERR_CUDA;
+  int grid = sms;
+  size_t smem = 0;
+  const bool clustered = rnnt_c4_plan(H, J, V1, Bmax, max_smem, &p, &grid, &smem);
+  if (!clustered) {
+    grid = sms;
+    const size_t fixed = rnnt_smem_fixed_bytes(H, J, V1, sms, Bmax, &p.umax, &p.pmax, &p.jmax);
+    const size_t room = static_cast<size_t>(max_smem) > fixed + fa.sharedSizeBytes ? max_smem - fixed - fa.sharedSizeBytes : 0;
+    const size_t useful = sizeof(float) * static_cast<size_t>(Bmax < kMaxTile ? (Bmax + 3) / 4 * 4 : kMaxTile) * (2 * H > J ? 2 * H : J);
+    const size_t need = sizeof(float) * static_cast<size_t>(4) * (2 * H > J ? 2 * H : J);  // one group of 4 utterances
+    if (room < need) return CFB_ERR_UNSUPPORTED;  // weights do not fit on chip
+    const size_t stage = (room < useful ? room : useful) / 16 * 16;
+    p.stage_floats = static_cast<int>(stage / sizeof(float));
+    smem = fixed + stage;
+    if (cudaFuncSetAttribute(rnnt_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+      return CFB_ERR_CUDA;
+  }
 
   // joint.enc over every frame: encp = encoded W_enc^T + b_enc on the tensor cores with split operands
   const bool xf32 = x_dtype == CFB_F32;
@@ -701,10 +1160,28 @@ int cfb_op_rnnt_greedy(const cfb_rnnt_weights* w, const void* encoded, int x_dty
     p.h_out = h_out + static_cast<size_t>(b0) * H;
     p.c_out = c_out + static_cast<size_t>(b0) * H;
     p.flags = flags;
-    void* args[] = {&p};
-    if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rnnt_greedy_kernel), dim3(sms), dim3(kThreads), args, smem, st) !=
-        cudaSuccess)
-      return CFB_ERR_CUDA;
+    if (clustered) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = kC;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeCooperative;
+      attr[1].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 2;
+      if (cudaLaunchKernelEx(&cfg, rnnt_greedy_c4_kernel, p) != cudaSuccess) return CFB_ERR_CUDA;
+    } else {
+      void* args[] = {&p};
+      if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rnnt_greedy_kernel), dim3(grid), dim3(kThreads), args, smem, st) !=
+          cudaSuccess)
+        return CFB_ERR_CUDA;
+    }
   }
   return cudaGetLastError() == cudaSuccess ? CFB_OK : CFB_ERR_CUDA;
 }
