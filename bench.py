@@ -303,7 +303,11 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
+    concurrent = [False]  # set once graphs with private workspaces are on: sub-batches overlap on side streams
+
     def step():
+        if concurrent[0]:
+            return enc.forward_many(dev_batches, args.streams)[-1]
         out = None
         for xd, ld in dev_batches:
             out = enc(audio_signal=xd, length=ld)
@@ -348,7 +352,8 @@ def run_b200(args):
     # cfb_forward is enqueue-only (no allocation, no sync), so the wrapper captures one graph per input shape and a
     # step = copy the inputs into the graph's static buffers (device to device) + one replay of ~260 kernel nodes.
     if not args.no_graphs:
-        enc.enable_cuda_graphs(True, max_shapes=max(4, len(dev_batches)))
+        concurrent[0] = args.streams > 1 and len(dev_batches) > 1
+        enc.enable_cuda_graphs(True, max_shapes=max(4, len(dev_batches)), private_workspaces=concurrent[0])
     for _ in range(3):
         step()
     barrier()
@@ -425,6 +430,33 @@ def run_b200(args):
         for k in range(n_buf):
             main_stream.wait_event(ev_done[k])
 
+    # Several sub-batches per step (cfg3) with graphs that own their workspaces: every sub-batch is a chain
+    # H2D -> forward (graph replay) -> D2H on ONE of `--streams` side streams, chains of different sub-batches overlap.
+    # Sub-batches of the same shape share a graph (static buffers), so they are kept on the same stream.
+    if concurrent[0]:
+        side = [torch.cuda.Stream(device=device) for _ in range(args.streams)]
+        x_dev = [torch.empty_like(x, device=device) for x, _ in host_batches]
+        l_dev = [torch.empty_like(ln, device=device) for _, ln in host_batches]
+        y_host = [torch.empty(bb, tt, d_out, dtype=torch.float32).pin_memory() for bb, tt in shapes]
+        yl_host = [torch.empty(bb, dtype=torch.int32).pin_memory() for bb, _ in shapes]
+        stream_of, lane_of = {}, []
+        for i, (x, _) in enumerate(host_batches):
+            lane_of.append(stream_of.setdefault(tuple(x.shape), i % args.streams))
+
+        def e2e_run(n_steps):  # noqa: F811 -- replaces the 2-deep pipeline above for this workload
+            for s in side:
+                s.wait_stream(main_stream)
+            for _ in range(n_steps):
+                for i, (xh, lh) in enumerate(host_batches):
+                    with torch.cuda.stream(side[lane_of[i]]):
+                        x_dev[i].copy_(xh, non_blocking=True)
+                        l_dev[i].copy_(lh, non_blocking=True)
+                        yy, ll = enc(audio_signal=x_dev[i], length=l_dev[i])
+                        y_host[i].copy_(yy.transpose(1, 2), non_blocking=True)
+                        yl_host[i].copy_(ll, non_blocking=True)
+            for s in side:
+                main_stream.wait_stream(s)
+
     e2e_run(2)
     barrier()
     e0.record()
@@ -434,7 +466,10 @@ def run_b200(args):
     seq_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
     e2e = {"value": audio_sec_job / (seq_ms / 1e3), "unit": UNIT, "ms_per_step": seq_ms,
-           "mode": "per sub-batch: pinned H2D of the features, ConformerEncoder.forward (CUDA graphs on), D2H of encoded "
+           "mode": (f"per sub-batch: pinned H2D of the features, ConformerEncoder.forward (CUDA graphs with private workspaces), D2H "
+                    f"of encoded + encoded_len, as one chain on one of {args.streams} side streams; chains of different "
+                    "sub-batches overlap") if concurrent[0] else
+                   "per sub-batch: pinned H2D of the features, ConformerEncoder.forward (CUDA graphs on), D2H of encoded "
                    "+ encoded_len; copies of neighbouring sub-batches overlap the forward on a second stream "
                    "(2-deep pipeline)",
            "h2d_bytes_per_step": sum(x.numel() * 4 + ln.numel() * 8 for x, ln in host_batches),
@@ -501,6 +536,7 @@ def run_b200(args):
     cfg = workload_config(args.workload, world)
     if extra_cfg:
         cfg.update(extra_cfg)
+        cfg["sub_batches_in_flight"] = args.streams if concurrent[0] else 1
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
@@ -589,6 +625,8 @@ def main():
     ap.add_argument("--bucket-frames", default="auto",
                     help="cfg3: length-bucket width in input frames, or auto (sharding.plan_cost picks it)")
     ap.add_argument("--max-batch", type=int, default=64, help="cfg3: utterances per sub-batch at most")
+    ap.add_argument("--streams", type=int, default=3,
+                    help="cfg3: sub-batches of a rank in flight at once (ConformerEncoder.forward_many); 1 = one after the other")
     ap.add_argument("--ncu", action="store_true", help="3 warm-up steps + 1 eager step only (for ncu -s/-c)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every step eagerly (no CUDA graph replay)")
     args = ap.parse_args()

@@ -218,15 +218,60 @@ class ConformerEncoder(nn.Module):
         return prev
 
     # ------------------------------------------------------------------------------------------------ CUDA graphs
-    def enable_cuda_graphs(self, on: bool = True, max_shapes: int = 4) -> None:
+    def enable_cuda_graphs(self, on: bool = True, max_shapes: int = 4, private_workspaces: bool = False) -> None:
         """cfb_forward only enqueues kernels (no allocation, no synchronisation), so a forward can be captured once
         per input shape and replayed: the ~260 launches of a step then cost one driver call.  With graphs on,
         ``forward`` copies its inputs into the graph's static buffers, replays, and returns views of the graph's
-        static output buffers -- they are overwritten by the next forward of the same shape."""
+        static output buffers -- they are overwritten by the next forward of the same shape.
+        ``private_workspaces``: every captured shape gets its own scratch workspace (instead of sharing the largest),
+        which is what lets graphs of different shapes run concurrently on different streams (``forward_many``)."""
         self._use_graphs = bool(on)
         self._graph_cap = max(1, int(max_shapes))
+        if bool(private_workspaces) != getattr(self, "_graph_private_ws", False):
+            self._graphs.clear()
+        self._graph_private_ws = bool(private_workspaces)
         if not on:
             self._graphs.clear()
+
+    @torch.no_grad()
+    def forward_many(self, batches, n_streams: int = 3):
+        """Independent sub-batches ``[(audio_signal, length), ...]`` (e.g. the length buckets of one rank,
+        sharding.plan_shards) run concurrently on up to ``n_streams`` side streams: a small sub-batch leaves most SMs
+        idle and its ~250 dependent launches are latency-bound, so overlapping sub-batches hides both.  Needs
+        ``enable_cuda_graphs(True, private_workspaces=True)``; otherwise (or for a single sub-batch) runs them one after
+        the other.  Returns ``[(encoded, encoded_len), ...]``; the caller's current stream waits for all of them."""
+        batches = list(batches)
+        if len(batches) <= 1 or n_streams <= 1 or self._profiling or \
+                not (self._use_graphs and getattr(self, "_graph_private_ws", False)):
+            return [self.forward(audio_signal=x, length=ln) for x, ln in batches]
+        device = batches[0][0].device
+        cur = torch.cuda.current_stream(device)
+        pool = self.__dict__.setdefault("_side_streams", [])
+        while len(pool) < n_streams:
+            pool.append(torch.cuda.Stream(device=device))
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        outs, owner = [], {}
+        for i, (x, ln) in enumerate(batches):
+            key = (tuple(x.shape), x.dtype, ln is not None)
+            if key in owner:  # same shape = same graph and static buffers: keep stream order, detach the earlier result
+                k, j = owner[key]
+                with torch.cuda.stream(pool[k]):
+                    outs[j] = (outs[j][0].clone(), outs[j][1].clone())
+            else:
+                k = i % n_streams
+            stream = pool[k]
+            if not any(o[0] == k for o in owner.values()):
+                stream.wait_event(fork)
+            with torch.cuda.stream(stream):
+                outs.append(self.forward(audio_signal=x, length=ln))
+            owner[key] = (k, i)
+        for k in {o[0] for o in owner.values()}:
+            cur.wait_stream(pool[k])
+        for enc_t, enc_len in outs:
+            enc_t.record_stream(cur)
+            enc_len.record_stream(cur)
+        return outs
 
     # ------------------------------------------------------------------------------------------------ weights
     def mark_weights_dirty(self) -> None:
@@ -354,6 +399,8 @@ class ConformerEncoder(nn.Module):
         key = (b, t, feats.dtype, length is not None, out_dtype, device.index)
         entry = self._graphs.get(key)
         if entry is None:
+            if getattr(self, "_graph_private_ws", False):
+                self._workspace = None  # this shape's graph gets a workspace no other graph touches
             static_feats = torch.empty_like(feats)
             static_len = torch.empty(b, dtype=torch.int64, device=device) if length is not None else None
             static_feats.copy_(feats)

@@ -379,3 +379,26 @@ def test_full_size_cfg5_long_form_bf16_against_fp32_validation_path():
     st = compare(y.cpu(), w.cpu(), ylen)
     assert st["nan"] == 0 and st["rel_l2"] <= 1e-2 and st["max_abs"] <= 5e-2, st
     assert ctc_agreement(y.cpu(), w.cpu(), ylen) >= 0.99
+
+
+def test_forward_many_runs_sub_batches_concurrently_and_bit_identically():
+    """ConformerEncoder.forward_many: the sub-batches of a rank on side streams (graphs with private workspaces) give
+    bit-identical results to running them one after the other, including two sub-batches of the same shape."""
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=2, d_model=256, n_heads=4)
+    sd = oc.random_state_dict(cfg, 53)
+    enc = build(cfg, sd, "bf16")
+    batches = []
+    for seed, (b, t, lens) in enumerate([(3, 400, [400, 391, 350]), (2, 240, [240, 201]), (5, 120, [120, 99, 80, 64, 7]),
+                                         (2, 240, [222, 240]), (1, 640, [640])]):
+        x, length = oc.synthetic_batch(b, 80, t, lens, seed=30 + seed)
+        batches.append((x.cuda(), length.cuda()))
+    want = [tuple(o.clone() for o in enc(audio_signal=x, length=ln)) for x, ln in batches]
+    enc.enable_cuda_graphs(True, max_shapes=8, private_workspaces=True)
+    for _ in range(3):  # first pass captures, later passes replay
+        got = enc.forward_many(batches, n_streams=3)
+        torch.cuda.synchronize()
+        assert len(got) == len(want)
+        for (y, yl), (w, wl) in zip(got, want):
+            assert torch.equal(yl, wl) and float((y - w).abs().max()) == 0.0
+    workspaces = {e[5].data_ptr() for e in enc._graphs.values()}
+    assert len(workspaces) == len(enc._graphs) == 4  # one private workspace per captured shape
