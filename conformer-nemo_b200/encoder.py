@@ -327,10 +327,13 @@ class ConformerEncoder(nn.Module):
                 _lib.load_library().cfb_destroy(self._handle)
             except Exception:  # pragma: no cover - interpreter shutdown
                 pass
-            self._handle = None
+            self.__dict__["_handle"] = None  # not through nn.Module.__setattr__: torch may already be torn down at exit
 
     def __del__(self):
-        self._destroy()
+        try:
+            self._destroy()
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
 
     # ------------------------------------------------------------------------------------------------ forward
     def output_frames(self, t: int) -> int:
