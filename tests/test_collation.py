@@ -163,3 +163,42 @@ def test_service_pinned_staging_on_gpu():
         assert b.audio_lengths.cpu().tolist() == [lengths[i] for i in b.indices]
         total += len(b.indices)
     assert total == len(svc.plan.rank_indices(1)) > 0
+
+
+def _gloo_collation_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lengths, load, svc = _service(world, rank, n=23, seed=9)
+    # the plan is derived from the lengths alone: no communication on the data path; the gather below is the test's own
+    mine = [(i, int(b.audio_lengths[row]), float(b.audio_signal[row].double().sum()))
+            for b in svc for row, i in enumerate(b.indices)]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    dist.barrier()
+    if rank == 0:
+        q.put((gathered, lengths))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_services_partition_the_manifest():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_collation_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered, lengths = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    flat = sorted(x for part in gathered for x in part)
+    assert [i for i, _, _ in flat] == list(range(23))                       # every utterance exactly once over the ranks
+    assert [n for _, n, _ in flat] == lengths
+    assert not ({i for i, _, _ in gathered[0]} & {i for i, _, _ in gathered[1]})
+    work = [sum(n for _, n, _ in part) for part in gathered]
+    assert max(work) <= 1.35 * min(work)                                    # LPT assignment balances the ranks
