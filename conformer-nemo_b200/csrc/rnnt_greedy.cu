@@ -446,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
             }
           }
           __syncthreads();
+          RNNT_TICK(11)
           const int ngr = (ns + 3) >> 2;  // tasks = (hidden unit: its 4 gate rows) x (group of 4 utterances)
           for (int task = warp; task < ngr * nu; task += kWarps) {
             const int grp = task % ngr, ul = task / ngr;
@@ -504,6 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_greedy_kernel(const RnntPara
           }
         }
         __syncthreads();
+        RNNT_TICK(12)
         const int npe = (ns + 1) >> 1;
         for (int task = warp; task < npe * nchunks; task += kWarps) {
           const int pr = task % npe, ch = task / npe, r0 = ch * 4;

@@ -259,3 +259,21 @@ class GreedyBatchedRNNTInfer:
             hyps.append(Hypothesis(score=float(scores[i]), y_sequence=tokens[i, :k].clone(), timestep=steps[i, :k].tolist(),
                                    dec_state=state, length=lens_cpu[i]))
         return (hyps,)
+
+
+class GreedyRNNTInfer(GreedyBatchedRNNTInfer):
+    """``decoding.strategy = greedy`` (rnnt_greedy_decoding.py:191-355): the reference decodes one utterance at a time with
+    the same per-utterance rule, so tokens, timesteps and scores are those of the batched decode (module docstring of
+    oracle/rnnt_oracle.py); here the whole batch still runs in one launch.  Differences in what the Hypothesis carries, kept:
+    ``dec_state`` is None for an utterance that emitted nothing (:277, :330-346) and ``last_token`` holds the last symbol."""
+
+    @torch.no_grad()
+    def forward(self, encoder_output: torch.Tensor, encoded_lengths: torch.Tensor,
+                partial_hypotheses: Optional[List[Hypothesis]] = None) -> Tuple[List[Hypothesis]]:
+        (hyps,) = super().forward(encoder_output, encoded_lengths, partial_hypotheses)
+        for h in hyps:
+            if len(h.y_sequence) == 0:
+                h.dec_state = None
+            else:
+                h.last_token = int(h.y_sequence[-1])
+        return (hyps,)

@@ -251,3 +251,9 @@ def load_reference_collation():
     coll = importlib.import_module("nemo.collections.common.parts.preprocessing.collections")
     a2t = importlib.import_module(name)
     return a2t, coll
+
+
+def load_reference_sample_greedy_class():
+    """The reference's sample-level ``GreedyRNNTInfer`` (rnnt_greedy_decoding.py:191), from the same unmodified module."""
+    load_reference_rnnt_classes()
+    return sys.modules["nemo.collections.asr.parts.submodules.rnnt_greedy_decoding"].GreedyRNNTInfer

@@ -80,6 +80,35 @@ def test_oracle_matches_live_reference_when_mounted():
         assert abs(h.score - r.score) <= 1e-4
 
 
+def test_sample_level_greedy_of_the_reference_gives_the_batched_hypotheses():
+    """decoding.strategy = greedy (one utterance at a time, rnnt_greedy_decoding.py:262-355) and greedy_batch agree on
+    tokens, timesteps and scores -- the premise of serving both through the one batched kernel."""
+    from oracle import reference_loader as rl
+
+    if not rl.reference_available():
+        pytest.skip("reference tree not mounted")
+    import warnings
+
+    dec_cls, joint_cls, batched_cls = rl.load_reference_rnnt_classes()
+    sample_cls = rl.load_reference_sample_greedy_class()
+    g = load("rnnt_tiny")
+    e, p, j, v = g["dims"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dec = dec_cls(prednet=dict(pred_hidden=p, pred_rnn_layers=1, dropout=0.1), vocab_size=v)
+    joint = joint_cls(jointnet=dict(encoder_hidden=e, pred_hidden=p, joint_hidden=j, activation=g["activation"], dropout=0.1),
+                      num_classes=v)
+    dec.load_state_dict(g["dec_sd"], strict=True)
+    joint.load_state_dict(g["joint_sd"], strict=True)
+    (a,) = sample_cls(dec, joint, blank_index=v, max_symbols_per_step=g["max_symbols"])(encoder_output=g["x"],
+                                                                                      encoded_lengths=g["lens"])
+    for b, h in enumerate(a):
+        n = int(g["n"][b])
+        assert h.y_sequence.tolist() == g["tokens"][b, :n].tolist() and list(h.timestep) == g["timesteps"][b, :n].tolist()
+        assert abs(h.score - float(g["scores"][b])) <= 1e-3
+        assert (h.dec_state is None) == (n == 0)
+
+
 def test_oracle_per_utterance_independence():
     g = load("rnnt_bpe128")
     full = ro.rnnt_greedy_decode(g["x"], g["lens"], g["dec_sd"], g["joint_sd"], g["max_symbols"], g["activation"], False)
@@ -278,3 +307,16 @@ def test_gpu_cluster_variant_matches_oracle(monkeypatch):
     _, _, greedy = build_modules(g["dims"], g["dec_sd"], g["joint_sd"], g["activation"], g["max_symbols"], "cuda")
     raw = ro.rnnt_greedy_decode(g["x"], g["lens"], g["dec_sd"], g["joint_sd"], g["max_symbols"], g["activation"], False)
     assert _compare(_decode_gpu(greedy, g["x"], g["lens"]), raw) == []
+
+
+@pytest.mark.gpu
+def test_gpu_sample_level_strategy_wrapper():
+    g = load("rnnt_tiny")
+    dec, joint, batched = build_modules(g["dims"], g["dec_sd"], g["joint_sd"], g["activation"], g["max_symbols"], "cuda")
+    single = cn.GreedyRNNTInfer(dec, joint, blank_index=g["dims"][3], max_symbols_per_step=g["max_symbols"])
+    a, b = _decode_gpu(single, g["x"], g["lens"]), _decode_gpu(batched, g["x"], g["lens"])
+    for i, (ha, hb) in enumerate(zip(a, b)):
+        n = int(g["n"][i])
+        assert ha.y_sequence.tolist() == hb.y_sequence.tolist() == g["tokens"][i, :n].tolist()
+        assert list(ha.timestep) == g["timesteps"][i, :n].tolist() and ha.score == hb.score
+        assert (ha.dec_state is None) == (n == 0) and (ha.last_token == (g["tokens"][i, n - 1] if n else None))

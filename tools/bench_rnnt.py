@@ -65,7 +65,7 @@ def main():
     out = greedy.decode_arrays(xg, lg)
     torch.cuda.synchronize()
     n_tok = out["n_tokens"].cpu()
-    phases = dict(zip(["joint", "barrier_joint", "control", "lstm", "barrier_lstm", "pred", "barrier_pred", "loop", "joint_stage", "joint_compute", "iterations"],
+    phases = dict(zip(["joint", "barrier_joint", "control", "lstm", "barrier_lstm", "pred", "barrier_pred", "loop", "joint_stage", "joint_compute", "iterations", "lstm_stage", "pred_stage"],
                       out["phase_cycles"].cpu().tolist()))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(args.warmup):
