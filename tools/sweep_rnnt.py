@@ -1,0 +1,69 @@
+"""Randomised parity sweep of the transducer greedy decode kernel against the CPU oracle (run on the GPU box):
+random sizes, batch sizes, lengths (incl. 0 and 1), max_symbols, activations, encoder-output dtypes, both kernel variants.
+
+    python tools/sweep_rnnt.py [n_cases] [seed]
+
+Prints one line per failing case and a JSON summary; exit code 1 if an utterance differs from the oracle anywhere but at a
+near-tie of the oracle's own arg-max (top-1 minus top-2 below 2e-6)."""
+import json
+import os
+import random
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import conformer_nemo_b200 as cn  # noqa: E402
+from oracle import rnnt_oracle as ro  # noqa: E402  (the checker)
+
+
+def main():
+    n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    rnd = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    bad, utts, symbols, clustered = [], 0, 0, 0
+    for case in range(n_cases):
+        e = rnd.choice([32, 48, 64, 176, 256, 512])
+        p = rnd.choice([32, 64, 96, 160, 320, 640])
+        j = rnd.choice([32, 48, 80, 320, 640])
+        v = rnd.choice([12, 28, 128, 500, 1024])
+        B, T = rnd.randint(1, 40), rnd.randint(1, 120)
+        ms = rnd.choice([1, 2, 3, 5, 10, 30])
+        act = rnd.choice(["relu", "relu", "tanh", "sigmoid"])
+        bias = rnd.uniform(0.0, 1.6)
+        lens = torch.tensor([rnd.choice([0, 1, T, rnd.randint(0, T)]) for _ in range(B)])
+        dec_sd, joint_sd = ro.random_rnnt_state_dicts(e, p, j, v, seed=1000 + case, blank_bias=bias)
+        x = torch.randn(B, e, T, generator=torch.Generator().manual_seed(case))
+        if rnd.random() < 0.3:
+            x = x.bfloat16()
+        use_cluster = rnd.random() < 0.4
+        os.environ["CFB_RNNT_CLUSTER"] = "1" if use_cluster else "0"
+        clustered += use_cluster
+        dec = cn.RNNTDecoder(prednet=dict(pred_hidden=p, pred_rnn_layers=1, dropout=0.1), vocab_size=v)
+        joint = cn.RNNTJoint(jointnet=dict(encoder_hidden=e, pred_hidden=p, joint_hidden=j, activation=act, dropout=0.1), num_classes=v)
+        dec.load_state_dict(dec_sd)
+        joint.load_state_dict(joint_sd)
+        greedy = cn.GreedyBatchedRNNTInfer(dec.cuda(), joint.cuda(), v, ms)
+        (hyps,) = greedy(encoder_output=x.cuda(), encoded_lengths=lens.cuda())
+        want = ro.rnnt_greedy_decode(x.float(), lens, dec_sd, joint_sd, ms, act, False)
+        for b, (h, r) in enumerate(zip(hyps, want)):
+            utts += 1
+            symbols += len(r.tokens)
+            if h.y_sequence.tolist() != r.tokens or list(h.timestep) != r.timesteps:
+                first = next((i for i, (a, c) in enumerate(zip(h.y_sequence.tolist(), r.tokens)) if a != c), min(len(h.y_sequence), len(r.tokens)))
+                # a difference is a near-tie if the oracle's own top-1 / top-2 gap at the first differing symbol is at the level of
+                # fp32 summation-order noise (the reference itself differs between its CPU and CUDA runs there)
+                margin = r.margins[first] if first < len(r.margins) else float("nan")
+                bad.append(dict(case=case, utt=b, dims=(e, p, j, v), B=B, T=T, max_symbols=ms, act=act, cluster=use_cluster,
+                                first_difference=first, got=len(h.y_sequence), want=len(r.tokens), oracle_margin_there=margin,
+                                near_tie=bool(margin < 2e-6)))
+                print("MISMATCH", bad[-1], flush=True)
+    real = [m for m in bad if not m["near_tie"]]
+    print(json.dumps(dict(cases=n_cases, clustered_cases=clustered, utterances=utts, symbols=symbols, mismatching_utterances=len(bad),
+                          of_which_near_ties=len(bad) - len(real))))
+    sys.exit(1 if real else 0)
+
+
+if __name__ == "__main__":
+    main()
