@@ -63,6 +63,51 @@ __global__ void __launch_bounds__(256) logsoftmax_argmax_kernel(const float* __r
   if (lane == 0 && best != nullptr) best[row] = mi;
 }
 
+// Greedy CTC collapse on the device (metrics/wer.py:152-164): per utterance keep frame t < len iff its arg-max p is not the
+// blank and differs from the previous frame's (the reference's `previous` starts as the blank).  One CTA per utterance:
+// keep flags -> block-wide exclusive scan (warp shuffles + one shared array) -> stable compaction in frame order.
+__global__ void __launch_bounds__(256) ctc_collapse_kernel(const int32_t* __restrict__ best, const int32_t* __restrict__ lens,
+                                                           int T, int blank, int32_t* __restrict__ tokens,
+                                                           int32_t* __restrict__ n_tokens) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int32_t* in = best + static_cast<long long>(b) * T;
+  int32_t* out = tokens + static_cast<long long>(b) * T;
+  int len = lens != nullptr ? lens[b] : T;
+  len = len < 0 ? 0 : (len > T ? T : len);
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < len; t0 += 256) {
+    const int t = t0 + tid;
+    int p = blank, prev = blank;
+    if (t < len) {
+      p = in[t];
+      prev = t > 0 ? in[t - 1] : blank;
+    }
+    const int keep = (t < len && p != blank && p != prev) ? 1 : 0;
+    int incl = keep;  // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (keep) out[before + incl - 1] = p;
+    __syncthreads();
+    if (tid == 0) {
+      int total = 0;
+      for (int w = 0; w < 8; ++w) total += s_warp[w];
+      s_base += total;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) n_tokens[b] = s_base;
+}
+
 std::string g_ctc_error;
 
 }  // namespace
@@ -115,6 +160,13 @@ int cfb_op_ctc_head(const void* x, int x_dtype, const void* W, const float* bias
   if (rc != 0) return CFB_ERR_CUDA;
   launch_pdl(logsoftmax_argmax_kernel, dim3((M + 7) / 8), dim3(256), 0, st, static_cast<const float*>(logits), ldl, logprobs,
              best, M, v1);
+  return cudaGetLastError() == cudaSuccess ? CFB_OK : CFB_ERR_CUDA;
+}
+
+int cfb_op_ctc_collapse(const int32_t* best, const int32_t* lens, int B, int T, int blank, int32_t* tokens, int32_t* n_tokens,
+                        cfb_stream stream) {
+  if (!best || !tokens || !n_tokens || B < 1 || T < 1) return CFB_ERR_INVALID_ARG;
+  ctc_collapse_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(best, lens, T, blank, tokens, n_tokens);
   return cudaGetLastError() == cudaSuccess ? CFB_OK : CFB_ERR_CUDA;
 }
 

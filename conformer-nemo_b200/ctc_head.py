@@ -76,7 +76,7 @@ class ConvASRDecoder(nn.Module):
         self._packed = (w, b, device)
 
     @torch.no_grad()
-    def forward_with_predictions(self, encoder_output: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward_with_predictions(self, encoder_output: torch.Tensor, _int32_predictions: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
         """(log_probs (B, T, V+1) fp32, greedy predictions (B, T) int64 = log_probs.argmax(-1), ctc_models.py:594)."""
         if encoder_output.dim() != 3 or encoder_output.size(1) != self._feat_in:
             raise TypeError(f"encoder_output must be (B, {self._feat_in}, T), got {tuple(encoder_output.shape)}")
@@ -106,15 +106,49 @@ class ConvASRDecoder(nn.Module):
                                      ctypes.c_void_p(sptr), need - 256,
                                      ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
         _lib.check(rc, None, "cfb_op_ctc_head")
-        return log_probs, best.long()
+        return log_probs, (best if _int32_predictions else best.long())
 
     def forward(self, encoder_output: torch.Tensor) -> torch.Tensor:
         return self.forward_with_predictions(encoder_output)[0]
 
+    @torch.no_grad()
+    def greedy_tokens(self, encoder_output: torch.Tensor, encoded_lengths: Optional[torch.Tensor] = None):
+        """features -> token ids without leaving the device: head, arg-max and the greedy collapse (metrics/wer.py:152-164).
+        Returns (tokens (B, T) int32, n_tokens (B) int32), both on the device; row b holds n_tokens[b] ids."""
+        _, pred = self.forward_with_predictions(encoder_output, _int32_predictions=True)
+        return ctc_collapse_device(pred, encoded_lengths, self._num_classes - 1)
+
+
+def ctc_collapse_device(predictions: torch.Tensor, lengths: Optional[torch.Tensor], blank_id: int):
+    """Greedy CTC collapse on the device (cfb_op_ctc_collapse): predictions (B, T) CUDA integer tensor, lengths (B) or None
+    -> (tokens (B, T) int32, n_tokens (B) int32) on the device.  Enqueue-only."""
+    if not predictions.is_cuda or predictions.dim() != 2:
+        raise RuntimeError("ctc_collapse_device needs a (B, T) CUDA tensor of arg-max classes")
+    device = predictions.device
+    pred = predictions.to(torch.int32).contiguous()
+    lens = None if lengths is None else lengths.to(device=device, dtype=torch.int32).contiguous()
+    b, t = pred.shape
+    tokens = torch.empty(b, t, dtype=torch.int32, device=device)
+    n_tokens = torch.empty(b, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        rc = _lib.load_library().cfb_op_ctc_collapse(
+            ctypes.c_void_p(pred.data_ptr()), ctypes.c_void_p(lens.data_ptr()) if lens is not None else None, b, t, int(blank_id),
+            ctypes.c_void_p(tokens.data_ptr()), ctypes.c_void_p(n_tokens.data_ptr()),
+            ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+    _lib.check(rc, None, "cfb_op_ctc_collapse")
+    return tokens, n_tokens
+
 
 def ctc_greedy_decode(predictions: torch.Tensor, lengths: Optional[Sequence[int]], blank_id: int) -> List[List[int]]:
-    """The greedy CTC collapse of metrics/wer.py:152-164 (host side, like the reference): per utterance cut at its
-    length, fold consecutive repeats, drop blanks."""
+    """The greedy CTC collapse of metrics/wer.py:152-164: per utterance cut at its length, fold consecutive repeats, drop
+    blanks.  CUDA predictions are collapsed on the device (one kernel, then one read of the ids); CPU predictions by the
+    reference's own host loop."""
+    if predictions.is_cuda:
+        lens_t = None if lengths is None else (lengths if torch.is_tensor(lengths) else torch.tensor(list(lengths)))
+        tokens, n_tokens = ctc_collapse_device(predictions, lens_t, blank_id)
+        n = n_tokens.cpu().tolist()
+        host = tokens[:, :max(max(n), 1)].cpu()
+        return [host[i, :k].tolist() for i, k in enumerate(n)]
     pred = predictions.long().cpu()
     lens = None if lengths is None else [int(v) for v in (lengths.cpu().tolist() if torch.is_tensor(lengths) else lengths)]
     out = []

@@ -220,6 +220,11 @@ CFB_API int cfb_op_lengths(const int64_t* lengths, int32_t* out, int B, int T_fu
 CFB_API size_t cfb_ctc_head_scratch_bytes(int M, int d, int v1);
 CFB_API int cfb_op_ctc_head(const void* x, int x_dtype, const void* W, const float* bias, int M, int d, int v1,
                     float* logprobs, int32_t* best, void* scratch, size_t scratch_bytes, cfb_stream stream);
+/* Greedy CTC collapse of the arg-max frames on the device (metrics/wer.py:152-164): per utterance b, the frames t < lens[b]
+ * (all T when lens == NULL) whose class is not `blank` and differs from the previous frame's are kept, in order.
+ *   best (B, T) int32;  tokens (B, T) int32 (the first n_tokens[b] entries of row b are valid);  n_tokens (B) int32. */
+CFB_API int cfb_op_ctc_collapse(const int32_t* best, const int32_t* lens, int B, int T, int blank, int32_t* tokens,
+                        int32_t* n_tokens, cfb_stream stream);
 
 /* ---- Transducer greedy decode on the encoder output (the transducer recipes' consumer) -------
  * RNNTDecoder.predict (modules/rnnt.py:190-283: Embedding with the blank as padding row + one LSTM layer), RNNTJoint.joint

@@ -119,3 +119,43 @@ def test_cuda_head_matches_oracle_on_encoder_like_input(b, t, d, v, dtype):
     got = cn.ctc_greedy_decode(pred, lens, v)
     ref = ho.greedy_collapse(lp.argmax(-1).cpu(), lens, v)
     assert got == ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,t,v,seed", [(1, 1, 4, 0), (3, 37, 5, 1), (32, 500, 1024, 2), (7, 700, 28, 3), (130, 257, 3, 4)])
+def test_gpu_collapse_kernel_equals_the_host_loop(b, t, v, seed):
+    """cfb_op_ctc_collapse against the reference's collapse loop (metrics/wer.py:152-164 as restated in the oracle): random
+    class streams with long blank / repeat runs, ragged lengths incl. 0, more frames than one 256-frame block."""
+    g = torch.Generator().manual_seed(seed)
+    pred = torch.randint(0, v + 1, (b, t), generator=g)
+    runs = torch.rand(b, t, generator=g) < 0.6               # make repeats and blank runs common
+    for i in range(1, t):
+        pred[:, i] = torch.where(runs[:, i], pred[:, i - 1], pred[:, i])
+    lens = torch.randint(0, t + 1, (b,), generator=g)
+    lens[0] = t
+    tokens, n = cn.ctc_collapse_device(pred.cuda(), lens.cuda(), v)
+    want = ho.greedy_collapse(pred, lens.tolist(), v)
+    n = n.cpu().tolist()
+    assert n == [len(w) for w in want]
+    host = tokens.cpu()
+    for i, w in enumerate(want):
+        assert host[i, :n[i]].tolist() == w
+    assert cn.ctc_greedy_decode(pred.cuda(), lens, v) == want
+    assert cn.ctc_greedy_decode(pred.cuda(), None, v) == ho.greedy_collapse(pred, None, v)
+
+
+@pytest.mark.gpu
+def test_gpu_features_to_token_ids_on_the_device():
+    d, v, b, t = 256, 128, 4, 90
+    sd = ho.random_head_state_dict(d, v, 21)
+    dec = cn.ConvASRDecoder(feat_in=d, num_classes=v)
+    dec.load_state_dict(sd)
+    dec = dec.cuda()
+    x = torch.randn(b, d, t, generator=torch.Generator().manual_seed(8)).cuda()
+    lens = torch.tensor([90, 61, 7, 0]).cuda()
+    tokens, n = dec.greedy_tokens(x, lens)
+    _, pred = dec.forward_with_predictions(x)
+    want = ho.greedy_collapse(pred.cpu(), lens.tolist(), v)
+    assert tokens.dtype == torch.int32 and tokens.is_cuda and n.cpu().tolist() == [len(w) for w in want]
+    for i, w in enumerate(want):
+        assert tokens[i, :len(w)].cpu().tolist() == w

@@ -95,7 +95,7 @@ def main():
         a, n = audio.to(dev, non_blocking=True), lengths.to(dev, non_blocking=True)
         y, yl = front(a, n)
         _, pred = head.forward_with_predictions(y)
-        return cn.ctc_greedy_decode(pred, yl, 1024)  # device -> host read + collapse on the host (metrics/wer.py:152-164)
+        return cn.ctc_greedy_decode(pred, yl, 1024)  # collapse kernel on the device (metrics/wer.py:152-164), then one read of the ids
 
     def run_rnnt():
         a, n = audio.to(dev, non_blocking=True), lengths.to(dev, non_blocking=True)
