@@ -28,8 +28,8 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxB = 128;  // utterances per launch (control state lives in shared memory)
 constexpr int kMaxTile = 32;  // utterances staged in shared memory at a time (the staging buffer takes what the weights leave)
-constexpr int kJointRound = 3;  // (e0, e1, q) float4 triples per thread and joint staging round
-constexpr int kStageRound = 5;  // float4 per thread and staging round: 5 x 512 x 4 floats = the whole staging buffer
+constexpr int kJointRound = 1;  // (e0, e1, q) float4 triples per thread and joint staging round
+constexpr int kStageRound = 2;  // float4 per thread and LSTM / pred staging round
 constexpr int kHardSymbolLimit = 4096;  // symbols per frame when max_symbols is unlimited (flag bit 1 if ever reached)
 
 struct RnntParams {
@@ -1017,7 +1017,7 @@ size_t rnnt_c4_fixed_bytes(int H, int J, int V1, int NQ, int B, int* umax, int* 
 // Plans the cluster variant: number of co-resident clusters, shared-memory split.  Returns false when it is not asked for
 // or the device / the sizes rule it out (the row-partitioned kernel is used then).
 bool rnnt_c4_plan(int H, int J, int V1, int Bmax, int max_smem, RnntParams* p, int* grid, size_t* smem) {
-  // opt-in (CFB_RNNT_CLUSTER=1): measured 12.6 ms against 13.5 ms for 32 x 500 frames, but the four-fold number of smaller
+  // opt-in (CFB_RNNT_CLUSTER=1): measured 11.3 ms against 12.1 ms for 32 x 500 frames, but the four-fold number of smaller
   // dot-product tiles costs what the smaller ingest saves once the batch grows
   const char* env = getenv("CFB_RNNT_CLUSTER");
   if (env == nullptr || atoi(env) == 0 || (H % 16) || (J % 16)) return false;
