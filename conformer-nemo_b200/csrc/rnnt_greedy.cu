@@ -1016,11 +1016,13 @@ size_t rnnt_c4_fixed_bytes(int H, int J, int V1, int NQ, int B, int* umax, int* 
 
 // Plans the cluster variant: number of co-resident clusters, shared-memory split.  Returns false when it is not asked for
 // or the device / the sizes rule it out (the row-partitioned kernel is used then).
+bool g_c4_unusable = false;  // set when a cooperative cluster launch was refused once (the other kernel serves from then on)
+
 bool rnnt_c4_plan(int H, int J, int V1, int Bmax, int max_smem, RnntParams* p, int* grid, size_t* smem) {
-  // opt-in (CFB_RNNT_CLUSTER=1): measured 11.3 ms against 12.1 ms for 32 x 500 frames, but the four-fold number of smaller
-  // dot-product tiles costs what the smaller ingest saves once the batch grows
+  // default; CFB_RNNT_CLUSTER=0 selects the row-partitioned kernel.  Measured (32 / 64 / 128 utterances x 500 frames):
+  // 11.3 / 17.2 / 29.5 ms against 12.1 / 19.1 / 32.8 ms
   const char* env = getenv("CFB_RNNT_CLUSTER");
-  if (env == nullptr || atoi(env) == 0 || (H % 16) || (J % 16)) return false;
+  if ((env != nullptr && atoi(env) == 0) || g_c4_unusable || (H % 16) || (J % 16)) return false;
   cudaFuncAttributes fa;
   if (cudaFuncGetAttributes(&fa, rnnt_greedy_c4_kernel) != cudaSuccess) return false;
   const size_t budget = static_cast<size_t>(max_smem) - fa.sharedSizeBytes;
@@ -1099,8 +1101,10 @@ int cfb_op_rnnt_greedy(const cfb_rnnt_weights* w, const void* encoded, int x_dty
   const int Bmax = B < kMaxB ? B : kMaxB;
   int grid = sms;
   size_t smem = 0;
-  const bool clustered = rnnt_c4_plan(H, J, V1, Bmax, max_smem, &p, &grid, &smem);
-  if (!clustered) {
+  bool clustered = false;
+  auto plan = [&]() -> int {
+    clustered = rnnt_c4_plan(H, J, V1, Bmax, max_smem, &p, &grid, &smem);
+    if (clustered) return CFB_OK;
     grid = sms;
     const size_t fixed = rnnt_smem_fixed_bytes(H, J, V1, sms, Bmax, &p.umax, &p.pmax, &p.jmax);
     const size_t room = static_cast<size_t>(max_smem) > fixed + fa.sharedSizeBytes ? max_smem - fixed - fa.sharedSizeBytes : 0;
@@ -1112,7 +1116,9 @@ int cfb_op_rnnt_greedy(const cfb_rnnt_weights* w, const void* encoded, int x_dty
     smem = fixed + stage;
     if (cudaFuncSetAttribute(rnnt_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return CFB_ERR_CUDA;
-  }
+    return CFB_OK;
+  };
+  if (int rc = plan()) return rc;
 
   // joint.enc over every frame: encp = encoded W_enc^T + b_enc on the tensor cores with split operands
   const bool xf32 = x_dtype == CFB_F32;
@@ -1177,8 +1183,13 @@ int cfb_op_rnnt_greedy(const cfb_rnnt_weights* w, const void* encoded, int x_dty
       attr[1].val.cooperative = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 2;
-      if (cudaLaunchKernelEx(&cfg, rnnt_greedy_c4_kernel, p) != cudaSuccess) return CFB_ERR_CUDA;
-    } else {
+      if (cudaLaunchKernelEx(&cfg, rnnt_greedy_c4_kernel, p) != cudaSuccess) {
+        cudaGetLastError();      // refused (e.g. the clusters are not co-resident right now): nothing was enqueued
+        g_c4_unusable = true;
+        if (int rc = plan()) return rc;
+      }
+    }
+    if (!clustered) {
       void* args[] = {&p};
       if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rnnt_greedy_kernel), dim3(grid), dim3(kThreads), args, smem, st) !=
           cudaSuccess)

@@ -37,7 +37,7 @@ def main():
         x = torch.randn(B, e, T, generator=torch.Generator().manual_seed(case))
         if rnd.random() < 0.3:
             x = x.bfloat16()
-        use_cluster = rnd.random() < 0.4
+        use_cluster = rnd.random() < 0.5
         os.environ["CFB_RNNT_CLUSTER"] = "1" if use_cluster else "0"
         clustered += use_cluster
         dec = cn.RNNTDecoder(prednet=dict(pred_hidden=p, pred_rnn_layers=1, dropout=0.1), vocab_size=v)
