@@ -289,23 +289,21 @@ def test_gpu_transducer_pipeline_waveform_to_hypotheses():
 
 @pytest.mark.gpu
 def test_gpu_both_kernel_variants_match_oracle(monkeypatch):
-    """The default kernel splits the weights over K inside clusters of 4 CTAs and adds the partial sums through distributed
-    shared memory (rnnt_greedy_c4_kernel); CFB_RNNT_CLUSTER=0 selects the row-partitioned one (rnnt_greedy_kernel, also the
-    fallback for sizes that are not multiples of 16).  Same hypotheses as the oracle from both."""
+    """CFB_RNNT_CLUSTER=1 selects the kernel that splits the weights over K inside clusters of 4 CTAs and adds the partial
+    sums through distributed shared memory (rnnt_greedy_c4_kernel); the default is the row-partitioned one
+    (rnnt_greedy_kernel).  Same hypotheses as the oracle from both."""
     dims = (512, 640, 640, 1024)
     dec_sd, joint_sd = ro.random_rnnt_state_dicts(*dims, seed=61, blank_bias=1.1)
     gen = torch.Generator().manual_seed(61)
     x = torch.randn(7, 512, 120, generator=gen)
     lens = torch.tensor([120, 97, 120, 64, 33, 2, 120])
     _, _, greedy = build_modules(dims, dec_sd, joint_sd, "relu", 30, "cuda")
-    clustered = _decode_gpu(greedy, x, lens)
-    monkeypatch.setenv("CFB_RNNT_CLUSTER", "0")
     base = _decode_gpu(greedy, x, lens)
-    monkeypatch.delenv("CFB_RNNT_CLUSTER")
+    monkeypatch.setenv("CFB_RNNT_CLUSTER", "1")
+    clustered = _decode_gpu(greedy, x, lens)
     want = ro.rnnt_greedy_decode(x, lens, dec_sd, joint_sd, 30, "relu", False)
     assert sum(len(r.tokens) for r in want) > 20
     assert _compare(clustered, want) == [] and _compare(base, want) == []
-    monkeypatch.setenv("CFB_RNNT_CLUSTER", "0")
     g = load("rnnt_bpe128")  # sizes where some ranks of a cluster own no row
     _, _, greedy = build_modules(g["dims"], g["dec_sd"], g["joint_sd"], g["activation"], g["max_symbols"], "cuda")
     raw = ro.rnnt_greedy_decode(g["x"], g["lens"], g["dec_sd"], g["joint_sd"], g["max_symbols"], g["activation"], False)
