@@ -287,27 +287,47 @@ def test_gpu_transducer_pipeline_waveform_to_hypotheses():
     assert seen == 5
 
 
+_CLUSTER_SCRIPT = r"""
+import os, sys, torch
+sys.path.insert(0, os.environ["CFB_TEST_ROOT"])
+sys.path.insert(0, os.path.join(os.environ["CFB_TEST_ROOT"], "tests"))
+import test_rnnt as t
+from oracle import rnnt_oracle as ro
+dims = (512, 640, 640, 1024)
+dec_sd, joint_sd = ro.random_rnnt_state_dicts(*dims, seed=61, blank_bias=1.1)
+gen = torch.Generator().manual_seed(61)
+x = torch.randn(7, 512, 120, generator=gen)
+lens = torch.tensor([120, 97, 120, 64, 33, 2, 120])
+_, _, greedy = t.build_modules(dims, dec_sd, joint_sd, "relu", 30, "cuda")
+want = ro.rnnt_greedy_decode(x, lens, dec_sd, joint_sd, 30, "relu", False)
+assert sum(len(r.tokens) for r in want) > 20
+os.environ["CFB_RNNT_CLUSTER"] = "0"
+assert t._compare(t._decode_gpu(greedy, x, lens), want) == []
+os.environ["CFB_RNNT_CLUSTER"] = "1"
+assert t._compare(t._decode_gpu(greedy, x, lens), want) == []
+g = t.load("rnnt_bpe128")  # sizes where some ranks of a cluster own no row
+_, _, greedy = t.build_modules(g["dims"], g["dec_sd"], g["joint_sd"], g["activation"], g["max_symbols"], "cuda")
+raw = ro.rnnt_greedy_decode(g["x"], g["lens"], g["dec_sd"], g["joint_sd"], g["max_symbols"], g["activation"], False)
+assert t._compare(t._decode_gpu(greedy, g["x"], g["lens"]), raw) == []
+print("CLUSTER_VARIANT_OK")
+"""
+
+
 @pytest.mark.gpu
-def test_gpu_both_kernel_variants_match_oracle(monkeypatch):
+def test_gpu_both_kernel_variants_match_oracle():
     """CFB_RNNT_CLUSTER=1 selects the kernel that splits the weights over K inside clusters of 4 CTAs and adds the partial
     sums through distributed shared memory (rnnt_greedy_c4_kernel); the default is the row-partitioned one
-    (rnnt_greedy_kernel).  Same hypotheses as the oracle from both."""
-    dims = (512, 640, 640, 1024)
-    dec_sd, joint_sd = ro.random_rnnt_state_dicts(*dims, seed=61, blank_bias=1.1)
-    gen = torch.Generator().manual_seed(61)
-    x = torch.randn(7, 512, 120, generator=gen)
-    lens = torch.tensor([120, 97, 120, 64, 33, 2, 120])
-    _, _, greedy = build_modules(dims, dec_sd, joint_sd, "relu", 30, "cuda")
-    base = _decode_gpu(greedy, x, lens)
-    monkeypatch.setenv("CFB_RNNT_CLUSTER", "1")
-    clustered = _decode_gpu(greedy, x, lens)
-    want = ro.rnnt_greedy_decode(x, lens, dec_sd, joint_sd, 30, "relu", False)
-    assert sum(len(r.tokens) for r in want) > 20
-    assert _compare(clustered, want) == [] and _compare(base, want) == []
-    g = load("rnnt_bpe128")  # sizes where some ranks of a cluster own no row
-    _, _, greedy = build_modules(g["dims"], g["dec_sd"], g["joint_sd"], g["activation"], g["max_symbols"], "cuda")
-    raw = ro.rnnt_greedy_decode(g["x"], g["lens"], g["dec_sd"], g["joint_sd"], g["max_symbols"], g["activation"], False)
-    assert _compare(_decode_gpu(greedy, g["x"], g["lens"]), raw) == []
+    (rnnt_greedy_kernel).  Same hypotheses as the oracle from both.  Runs in a child process: tools that intercept launches
+    (Nsight Compute) abort a process on a cooperative cluster launch, which must not take the test session with it."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CFB_TEST_ROOT=root)
+    r = subprocess.run([sys.executable, "-c", _CLUSTER_SCRIPT], capture_output=True, text=True, env=env, timeout=600)
+    if r.returncode != 0 and "Traceback" not in r.stderr:  # killed from outside, not a Python failure of the checks above
+        pytest.skip("cooperative cluster launch not available in this environment: " + r.stderr[-300:])
+    assert r.returncode == 0 and "CLUSTER_VARIANT_OK" in r.stdout, r.stderr[-2000:]
 
 
 @pytest.mark.gpu
