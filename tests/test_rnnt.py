@@ -152,8 +152,14 @@ def _compare(hyps, want, score_tol=2e-4, state_tol=2e-5):
     """tokens / timesteps exact; scores and states to fp32 rounding.  `want`: list of oracle results."""
     bad = []
     for b, (h, r) in enumerate(zip(hyps, want)):
-        if h.y_sequence.tolist() != r.tokens or list(h.timestep) != r.timesteps:
-            bad.append(b)
+        got = h.y_sequence.tolist()
+        if got != r.tokens or list(h.timestep) != r.timesteps:
+            # Not a failure only if the oracle itself is undecided there: its top-1 / top-2 joint outputs at the first differing
+            # symbol are within fp32 summation-order noise (the oracle's arithmetic depends on the host CPU's BLAS kernels, the
+            # kernel's does not), after which an autoregressive decode legitimately continues differently.
+            first = next((i for i, (a, c) in enumerate(zip(got, r.tokens)) if a != c), min(len(got), len(r.tokens)))
+            if not (first < len(r.margins) and r.margins[first] < 2e-6):
+                bad.append(b)
             continue
         assert abs(h.score - r.score) <= score_tol * max(1.0, abs(r.score)), (b, h.score, r.score)
         if h.dec_state is not None:
