@@ -7,6 +7,9 @@
 A step = one forward pass of the encoder over one synthetic batch.  Workload at every N: BASELINE.json configs[1],
 Conformer-CTC Large encoder (d_model 512, 17 layers, 8 heads, ff x4, striding x4), batch 32 x 20 s (T = 2000 mel
 frames, full lengths) PER GPU (weak scaling, utterances are independent, no data-path collective).
+The same line carries `strong`: BASELINE.json configs[2] (cfg3) measured with the same encoder in the same process --
+ONE global batch of 64 mixed-length utterances (2-30 s) LPT-sharded over the N ranks, every rank running its share in
+the packed variable-length layout (cfb_forward_packed): the strong-scaling curve of the split the north star names.
 
 Printed JSON (one line, rank 0):
   value     whole-job audio-s/s with inputs resident in HBM, CUDA-event timed, max over ranks
@@ -237,12 +240,16 @@ GEMM_LABELS = ["pre_encode.out", "linear_pos", "qkv projection", "linear_out", "
                "linear1+swish", "linear2"]  # the fused depthwise+pointwise_conv2 kernel is not gemm_tc_kernel: reported apart
 
 
-def build_batches(args, kw, rank, world):
+def _pin(t):
+    return t.pin_memory() if torch.cuda.is_available() else t  # the reference arm also runs on GPU-less hosts
+
+
+def build_batches(args, kw, rank, world, name=None):
     """The rank's sub-batches for one step: [(features (B, F, T) pinned host, lengths (B,) pinned host), ...].
     cfg3 (strong scaling): one global batch of 64 mixed-length utterances, planned over `world` ranks by
     conformer_nemo_b200.sharding.plan_shards (LPT assignment + length buckets, no communication).
     Every other workload (weak scaling): the same single full-length batch on every rank."""
-    name = args.workload
+    name = name or args.workload
     if WORKLOADS[name][1] is None:
         import random
 
@@ -251,6 +258,8 @@ def build_batches(args, kw, rank, world):
         rnd = random.Random(1234)  # len ~ U[200, 3000] frames, seed 1234
         lengths = [rnd.randint(200, 3000) for _ in range(64)]
         bucket = args.bucket_frames if args.bucket_frames == "auto" else int(args.bucket_frames)
+        if args.packed != "off" and args.bucket_frames == "auto":
+            bucket = 1 << 30  # packed layout: padding costs nothing, so a rank's share is ONE sub-batch (one launch set)
         plan = plan_shards(lengths, world, max_batch=args.max_batch, bucket_frames=bucket)
         g = torch.Generator().manual_seed(1234)
         out = []
@@ -259,94 +268,64 @@ def build_batches(args, kw, rank, world):
             x = torch.zeros(len(sub), kw["feat_in"], max(lens))
             for row, n in enumerate(lens):
                 x[row, :, :n] = torch.randn(kw["feat_in"], n, generator=g)
-            out.append((x.pin_memory(), torch.tensor(lens, dtype=torch.int64).pin_memory()))
+            out.append((_pin(x), _pin(torch.tensor(lens, dtype=torch.int64))))
         return out, sum(lengths) * FRAME_SEC, "strong", {"utterances": 64, "frames": "U[200,3000] seed 1234",
                                                          "sub_batches_rank0": len(out), "bucket_frames": args.bucket_frames,
-                                                         "max_batch": args.max_batch}
+                                                         "max_batch": args.max_batch,
+                                                         "layout": "dense (padded sub-batches)" if args.packed == "off"
+                                                         else "packed (cfb_forward_packed: one slot of token rows per utterance, no padding)"}
     _, b, t = WORKLOADS[name]
     g = torch.Generator().manual_seed(1234 + rank)
-    x = torch.randn(b, kw["feat_in"], t, generator=g).pin_memory()
-    ln = torch.full((b,), t, dtype=torch.int64).pin_memory()
+    x = _pin(torch.randn(b, kw["feat_in"], t, generator=g))
+    ln = _pin(torch.full((b,), t, dtype=torch.int64))
     return [(x, ln)], b * t * FRAME_SEC * world, "weak", None
 
 
-def run_b200(args):
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference)")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        # rank 0 prints exactly one JSON line on stdout: NCCL's own output (version banner at WARN/INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=device)
-    kw = WORKLOADS[args.workload][0]
-    enc = build_encoder(kw, device)
-    host_batches, audio_sec_job, scaling, extra_cfg = build_batches(args, kw, rank, world)
-    dev_batches = [(x.to(device), ln.to(device)) for x, ln in host_batches]
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if dist is None:
-            return ms
-        tt = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
-
+def measure_workload(enc, args, host_batches, audio_sec_job, device, barrier, max_over_ranks, sampler=None,
+                     eager=True):
+    """Times one workload on this rank's sub-batches: device-resident steps launched eagerly, then through CUDA-graph
+    replay (the headline), then end to end with host buffers.  Returns a dict; every time is the max over ranks."""
+    use_host_lens = args.packed != "off"
+    enc.packed = True if args.packed == "on" else "auto"
+    dev_batches = [(x.to(device), ln.to(device), ln.tolist() if use_host_lens else None) for x, ln in host_batches]
+    main_stream = torch.cuda.current_stream(device)
     concurrent = [False]  # set once graphs with private workspaces are on: sub-batches overlap on side streams
 
     def step():
         if concurrent[0]:
             return enc.forward_many(dev_batches, args.streams)[-1]
         out = None
-        for xd, ld in dev_batches:
-            out = enc(audio_signal=xd, length=ld)
+        for xd, ld, hl in dev_batches:
+            out = enc(audio_signal=xd, length=ld, length_host=hl)
         return out
 
-    # ---------------- device-resident throughput
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    enc.enable_cuda_graphs(False)
     launches_per_step = 0
     for i in range(max(args.warmup, 3)):
-        for xd, ld in dev_batches:
-            enc(audio_signal=xd, length=ld)
+        for xd, ld, hl in dev_batches:
+            enc(audio_signal=xd, length=ld, length_host=hl)
             if i == 0:
                 launches_per_step += enc.last_launch_count()
     if args.ncu:
-        # profiling helper: 3 warm-up steps above, ONE eager step here, nothing else (no graphs, no e2e, no JSON):
-        #   ncu -s <3 * launches/step> -c <launches/step> ... python bench.py --ncu
-        step()
-        torch.cuda.synchronize()
-        if rank == 0:
-            emit({"ncu_helper": True, "launches_per_step": launches_per_step})
-        return
+        return {"step": step, "launches_per_step": launches_per_step}
     # a fresh box needs a moment of sustained load before clocks / power state settle: keep warming for ~1 s
     torch.cuda.synchronize()
     t_warm = time.time()
-    while time.time() - t_warm < 1.0:
+    while time.time() - t_warm < args.settle:
         step()
         torch.cuda.synchronize()
 
-    # ---------------- the steps launched eagerly (host-side launch cost included); reported beside the headline
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    eager_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    eager_ms = None
+    if eager:
+        # ---------------- the steps launched eagerly (host-side launch cost included); reported beside the headline
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        eager_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
     # ---------------- headline: the public forward with CUDA graphs on (ConformerEncoder.enable_cuda_graphs).
     # cfb_forward is enqueue-only (no allocation, no sync), so the wrapper captures one graph per input shape and a
@@ -357,7 +336,7 @@ def run_b200(args):
     for _ in range(3):
         step()
     barrier()
-    if rank == 0:
+    if sampler is not None:
         sampler.mark()
     e0.record()
     for _ in range(args.steps):
@@ -365,7 +344,7 @@ def run_b200(args):
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
     ms_step = ms_total / args.steps
     value = audio_sec_job / (ms_step / 1e3)
 
@@ -376,8 +355,8 @@ def run_b200(args):
     n_buf = 2
     shapes = [(x.shape[0], enc.output_frames(x.shape[2])) for x, _ in host_batches]
     d_out = y.shape[1]
-    max_b = max(s[0] for s in shapes)
-    max_bt = max(s[0] * s[1] for s in shapes)
+    max_b = max(sh[0] for sh in shapes)
+    max_bt = max(sh[0] * sh[1] for sh in shapes)
     max_in = max(x.numel() for x, _ in host_batches)
     out_host = [torch.empty(max_bt * d_out, dtype=torch.float32).pin_memory() for _ in range(n_buf)]
     olen_host = [torch.empty(max_b, dtype=torch.int32).pin_memory() for _ in range(n_buf)]
@@ -386,12 +365,12 @@ def run_b200(args):
     y_stage = [torch.empty(max_bt * d_out, dtype=torch.float32, device=device) for _ in range(n_buf)]
     ylen_stage = [torch.empty(max_b, dtype=torch.int32, device=device) for _ in range(n_buf)]
     copy_stream = torch.cuda.Stream(device=device)
-    main_stream = torch.cuda.current_stream(device)
     ev_in = [torch.cuda.Event() for _ in range(n_buf)]        # features of the slot are on the device
     ev_used = [torch.cuda.Event() for _ in range(n_buf)]      # the forward has consumed the slot's features
     ev_out = [torch.cuda.Event() for _ in range(n_buf)]       # the slot's result is in y_stage
     ev_done = [torch.cuda.Event() for _ in range(n_buf)]      # the slot's result is in host memory
     n_sub = len(host_batches)
+    host_lens = [ln.tolist() if use_host_lens else None for _, ln in host_batches]
 
     def e2e_run(n_steps):
         total = n_steps * n_sub
@@ -416,7 +395,8 @@ def run_b200(args):
             if i + 1 < total:
                 h2d(i + 1)
             main_stream.wait_event(ev_in[k])
-            yy, ll = enc(audio_signal=x_stage[k][: xh.numel()].view_as(xh), length=len_stage[k][: lh.numel()])
+            yy, ll = enc(audio_signal=x_stage[k][: xh.numel()].view_as(xh), length=len_stage[k][: lh.numel()],
+                         length_host=host_lens[i % n_sub])
             ev_used[k].record(main_stream)
             main_stream.wait_event(ev_done[k])            # the slot's previous result has left the device
             y_stage[k][: bb * tt * d_out].view(bb, tt, d_out).copy_(yy.transpose(1, 2))
@@ -440,22 +420,22 @@ def run_b200(args):
         y_host = [torch.empty(bb, tt, d_out, dtype=torch.float32).pin_memory() for bb, tt in shapes]
         yl_host = [torch.empty(bb, dtype=torch.int32).pin_memory() for bb, _ in shapes]
         stream_of, lane_of = {}, []
-        for i, (x, _) in enumerate(host_batches):
-            lane_of.append(stream_of.setdefault(tuple(x.shape), i % args.streams))
+        for i, (x, ln) in enumerate(host_batches):
+            lane_of.append(stream_of.setdefault((tuple(x.shape), tuple(ln.tolist())), i % args.streams))
 
         def e2e_run(n_steps):  # noqa: F811 -- replaces the 2-deep pipeline above for this workload
-            for s in side:
-                s.wait_stream(main_stream)
+            for sd_ in side:
+                sd_.wait_stream(main_stream)
             for _ in range(n_steps):
                 for i, (xh, lh) in enumerate(host_batches):
                     with torch.cuda.stream(side[lane_of[i]]):
                         x_dev[i].copy_(xh, non_blocking=True)
                         l_dev[i].copy_(lh, non_blocking=True)
-                        yy, ll = enc(audio_signal=x_dev[i], length=l_dev[i])
+                        yy, ll = enc(audio_signal=x_dev[i], length=l_dev[i], length_host=host_lens[i])
                         y_host[i].copy_(yy.transpose(1, 2), non_blocking=True)
                         yl_host[i].copy_(ll, non_blocking=True)
-            for s in side:
-                main_stream.wait_stream(s)
+            for sd_ in side:
+                main_stream.wait_stream(sd_)
 
     e2e_run(2)
     barrier()
@@ -474,6 +454,66 @@ def run_b200(args):
                    "(2-deep pipeline)",
            "h2d_bytes_per_step": sum(x.numel() * 4 + ln.numel() * 8 for x, ln in host_batches),
            "d2h_bytes_per_step": sum(bb * tt * d_out * 4 + bb * 4 for bb, tt in shapes)}
+    return {"value": value, "ms_per_step": ms_step, "eager_ms_per_step": eager_ms, "e2e": e2e, "clocks": clocks,
+            "launches_per_step": launches_per_step, "step": step, "sub_batches_in_flight": args.streams if concurrent[0] else 1}
+
+
+def packing_stats(enc, host_batches):
+    """Token rows the step computes on: dense = sum B * T'max of the sub-batches, packed = the slots, valid = sum T'_b."""
+    dense = sum(x.shape[0] * enc.output_frames(x.shape[2]) for x, _ in host_batches)
+    packed = sum(enc.packed_rows(ln.tolist(), x.shape[2]) for x, ln in host_batches)
+    valid = sum(_out_frames(int(n))[1] for _, ln in host_batches for n in ln.tolist())
+    return {"token_rows_valid": valid, "token_rows_packed": packed, "token_rows_dense": dense}
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        # rank 0 prints exactly one JSON line on stdout: NCCL's own output (version banner at WARN/INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=device)
+    kw = WORKLOADS[args.workload][0]
+    enc = build_encoder(kw, device)
+    host_batches, audio_sec_job, scaling, extra_cfg = build_batches(args, kw, rank, world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        tt = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---------------- device-resident throughput + end to end (the headline workload)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    head = measure_workload(enc, args, host_batches, audio_sec_job, device, barrier, max_over_ranks,
+                            sampler if rank == 0 else None)
+    step = head["step"]
+    if args.ncu:
+        # profiling helper: 3 warm-up steps above, ONE eager step here, nothing else (no graphs, no e2e, no JSON):
+        #   ncu -s <3 * launches/step> -c <launches/step> ... python bench.py --ncu
+        step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            emit({"ncu_helper": True, "launches_per_step": head["launches_per_step"]})
+        return
+    launches_per_step = head["launches_per_step"]
 
     # ---------------- per-kernel timing pass (CUDA events on the forward's stream) -> roofline
     roofline, kernels = None, None
@@ -521,12 +561,42 @@ def run_b200(args):
                     "share_of_step": round(gemm_ms / sum(v[1] for v in rep.values()) * prof_steps, 4),
                     "how": f"CUDA events around every launch, {prof_steps} extra steps after the timed region"}
 
-    # ---------------- CPU baseline (oracle = CPU port of the reference algorithm), bounded sample, N=1 rank 0 only
+    # ---------------- strong scaling of the split the north star names (cfg3), same encoder, same process
+    strong = None
+    if args.strong and WORKLOADS[args.workload][0] == WORKLOADS["cfg3"][0] and WORKLOADS[args.workload][1] is not None:
+        s_batches, s_audio, _, s_cfg = build_batches(args, kw, rank, world, name="cfg3")
+        sm = measure_workload(enc, args, s_batches, s_audio, device, barrier, max_over_ranks, None, eager=False)
+        stats = packing_stats(enc, s_batches)
+        strong = {"workload": workload_config("cfg3", world)["workload"], "metric": METRIC, "unit": UNIT,
+                  "value": sm["value"], "ms_per_step": sm["ms_per_step"], "n_gpus": world, "steps": args.steps,
+                  "scaling": "strong", "audio_sec_per_step": s_audio, "e2e": sm["e2e"],
+                  "sub_batches_rank0": len(s_batches), "sub_batches_in_flight": sm["sub_batches_in_flight"],
+                  "launches_per_step_rank0": sm["launches_per_step"], "rank0": stats, **(s_cfg or {})}
+        if world == 1 and args.strong_sim:
+            # what every rank of a 2 / 4 / 8-GPU job would run, measured one share after the other on THIS GPU (the path
+            # has no communication, so a rank's time does not depend on the others); the slowest share sets the step
+            sim = {}
+            for w in (2, 4, 8):
+                worst, per_rank = 0.0, []
+                for r in range(w):
+                    rb, _, _, _ = build_batches(args, kw, r, w, name="cfg3")
+                    saved = (args.steps, args.settle)
+                    args.steps, args.settle = min(args.steps, 10), 0.0
+                    try:
+                        m = measure_workload(enc, args, rb, s_audio, device, barrier, max_over_ranks, None, eager=False)
+                    finally:
+                        args.steps, args.settle = saved
+                    per_rank.append(round(m["ms_per_step"], 4))
+                    worst = max(worst, m["ms_per_step"])
+                sim[str(w)] = {"ms_per_step_slowest_rank": worst, "value": s_audio / (worst / 1e3),
+                               "speedup_vs_1gpu": sm["ms_per_step"] / worst, "ms_per_rank": per_rank}
+            strong["emulated_on_one_gpu"] = sim
+
+    # ---------------- CPU baseline: the reference's own forward (or the oracle port) on the WHOLE workload batch, rank 0, N=1
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t_ref = int(host_batches[0][0].shape[2])
-        cpu_baseline = time_oracle(kw, {k: v.detach().float().cpu() for k, v in enc.state_dict().items()},
-                                   sample_b=min(2, host_batches[0][0].shape[0]), t=min(t_ref, 6000), warmup=1, steps=2)
+        cpu_baseline = time_cpu_arm(kw, {k: v.detach().float().cpu() for k, v in enc.state_dict().items()},
+                                    [(x, ln) for x, ln in host_batches], warmup=1, steps=2, budget_s=60.0)
 
     if dist is not None:
         dist.barrier()
@@ -536,64 +606,113 @@ def run_b200(args):
     cfg = workload_config(args.workload, world)
     if extra_cfg:
         cfg.update(extra_cfg)
-        cfg["sub_batches_in_flight"] = args.streams if concurrent[0] else 1
+        cfg["sub_batches_in_flight"] = head["sub_batches_in_flight"]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic (randn log-mel features, random-init weights)",
-        "config": cfg, "clocks": clocks, "e2e": e2e,
+        "config": cfg, "clocks": head["clocks"], "e2e": head["e2e"],
         "gpu_launches": launches_per_step * args.steps,
-        "launch_mode": "eager" if args.no_graphs else "cuda graph replay", "eager_ms_per_step": eager_ms,
-        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        "launch_mode": "eager" if args.no_graphs else "cuda graph replay", "eager_ms_per_step": head["eager_ms_per_step"],
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "strong": strong,
     }
     emit(line)
 
 
-def time_oracle(kw, sd, sample_b, t, warmup, steps):
-    """Times the oracle on the host cores.  The only place the benchmark touches oracle/ (cpu_baseline leg)."""
+def cpu_forward_fn(kw, sd):
+    """The CPU arm's forward: the reference's own unmodified ConformerEncoder when a reference tree is reachable
+    ($CONFORMER_REF, /root/reference, or the per-pod install baseline/_ref written by oracle/install_reference.py),
+    else the oracle port of its algorithm.  The only place the benchmark touches oracle/ (cpu_baseline / reference arm)."""
     from oracle import conformer_oracle as oc
+    from oracle import reference_loader as rl
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     cfg = oc.EncoderConfig(feat_in=kw["feat_in"], n_layers=kw["n_layers"], d_model=kw["d_model"], n_heads=kw["n_heads"])
     if sd is None:
         sd = oc.random_state_dict(cfg, 0)
     sd = {k: v for k, v in sd.items() if not k.endswith("num_batches_tracked")}
-    x, length = oc.synthetic_batch(sample_b, kw["feat_in"], t, None, seed=1234)
+    if rl.reference_available():
+        try:
+            ref = rl.build_reference_encoder(cfg, sd)
+
+            def fwd(x, length):
+                with torch.no_grad():
+                    return ref(audio_signal=x, length=length)
+
+            return fwd, "reference", f"unmodified ConformerEncoder.forward loaded from {rl.REFERENCE_ROOT}"
+        except Exception as e:  # pragma: no cover - fall back to the port, say why
+            why = f"reference at {rl.REFERENCE_ROOT} failed to load ({type(e).__name__}: {e}); oracle port timed instead"
+    else:
+        why = "no reference tree reachable (looked at $CONFORMER_REF, /root/reference, baseline/_ref, oracle/_ref); oracle port"
+    return (lambda x, length: oc.encoder_forward(sd, cfg, x, length)), "port", why
+
+
+def time_cpu_arm(kw, sd, batches, warmup, steps, budget_s):
+    """Times the CPU arm on the given sub-batches [(features (B, F, T), lengths (B,))] = one step of the workload.
+    `steps` timed steps after `warmup`, cut short (never below one step) once `budget_s` seconds have been spent."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fwd, kind, how = cpu_forward_fn(kw, sd)
+    batches = [(x.float(), ln.to(torch.int64)) for x, ln in batches]
+    audio = sum(float(ln.sum()) for _, ln in batches) * FRAME_SEC
+    t_begin = time.perf_counter()
+
+    def one_step():
+        t0 = time.perf_counter()
+        for x, ln in batches:
+            fwd(x, ln)
+        return time.perf_counter() - t0
+
+    done_w = 0
     for _ in range(warmup):
-        oc.encoder_forward(sd, cfg, x, length)
+        one_step()
+        done_w += 1
+        if time.perf_counter() - t_begin > budget_s / 2:
+            break
     times = []
     for _ in range(steps):
-        t0 = time.perf_counter()
-        oc.encoder_forward(sd, cfg, x, length)
-        times.append(time.perf_counter() - t0)
+        times.append(one_step())
+        if time.perf_counter() - t_begin > budget_s:
+            break
     sec = sum(times) / len(times)
-    return {"value": sample_b * t * FRAME_SEC / sec, "unit": UNIT, "cores": cores, "kind": "port",
-            "sec_per_step": sec,
-            "sample": f"{sample_b} of the workload's utterances x {t * FRAME_SEC:.0f} s, fp32, torch {torch.__version__} "
-                      f"CPU kernels, {cores} threads, mean of {steps} after {warmup} warm-up"}
+    cpu_model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            cpu_model = next((l.split(":", 1)[1].strip() for l in f if l.startswith("model name")), "")
+    except OSError:
+        pass
+    shape = ", ".join(f"{x.shape[0]} x {x.shape[2]} frames" for x, _ in batches[:4]) + (" ..." if len(batches) > 4 else "")
+    return {"value": audio / sec, "unit": UNIT, "cores": cores, "kind": kind, "sec_per_step": sec,
+            "steps": len(times), "warmup": done_w, "cpu_model": cpu_model, "how": how,
+            "sample": f"the whole workload step ({shape}; {audio:.0f} s of audio), fp32, torch {torch.__version__} CPU "
+                      f"kernels, {cores} threads, mean of {len(times)} after {done_w} warm-up"}
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU algorithm (oracle port; the reference package itself cannot be
-    imported -- hydra / pytorch_lightning / sox are absent -- and does not travel to the GPU box)."""
+    """Reference arm: the reference's own CPU implementation of the path on the host cores, on the b200 arm's config
+    (whole workload batch per step).  --steps / --warmup are honoured unless the run would exceed ~4 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    kw, b, t = WORKLOADS[args.workload]
-    if b is None:  # cfg3: two utterances of the mean length
-        b, t = 2, 1600
-    res = time_oracle(kw, None, sample_b=min(2, b), t=min(t, 6000), warmup=min(args.warmup, 2),
-                      steps=max(1, min(args.steps, 10)))
+    kw = WORKLOADS[args.workload][0]
+    host_batches, _, _, _ = build_batches(args, kw, 0, 1)
+    res = time_cpu_arm(kw, None, host_batches, warmup=max(1, args.warmup), steps=max(1, args.steps), budget_s=240.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
-        "steps": max(1, min(args.steps, 10)), "warmup": min(args.warmup, 2), "ms_per_step": res["sec_per_step"] * 1e3,
+        "steps": res["steps"], "warmup": res["warmup"], "ms_per_step": res["sec_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, world), "cpu_baseline": res,
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.workload == "cfg2":
+        # BASELINE.md section 3: cfg 1 (Small, d_model 176, 16 layers, 4 heads, 4 x 10 s) in full, the reference's own CPU case
+        kw1 = dict(feat_in=80, n_layers=16, d_model=176, n_heads=4)
+        g = torch.Generator().manual_seed(1234)
+        b1 = [(torch.randn(4, 80, 1000, generator=g), torch.full((4,), 1000, dtype=torch.int64))]
+        r1 = time_cpu_arm(kw1, None, b1, warmup=2, steps=5, budget_s=30.0)
+        line["cfg1"] = {"workload": "cfg1: Conformer-CTC Small encoder d_model=176 layers=16 heads=4, batch 4 x 10 s, fp32 on the host cores",
+                        **r1}
     emit(line)
 
 
@@ -627,6 +746,14 @@ def main():
     ap.add_argument("--max-batch", type=int, default=64, help="cfg3: utterances per sub-batch at most")
     ap.add_argument("--streams", type=int, default=3,
                     help="cfg3: sub-batches of a rank in flight at once (ConformerEncoder.forward_many); 1 = one after the other")
+    ap.add_argument("--packed", default="auto", choices=["auto", "on", "off"],
+                    help="variable-length layout (cfb_forward_packed) for mixed-length batches: auto = when it saves >= 15 %% "
+                         "of the token rows, off = dense padded sub-batches")
+    ap.add_argument("--no-strong", dest="strong", action="store_false",
+                    help="skip the cfg3 strong-scaling sub-record of the default (cfg2) line")
+    ap.add_argument("--no-strong-sim", dest="strong_sim", action="store_false",
+                    help="N=1: skip the one-GPU emulation of the 2/4/8-rank shares of cfg3")
+    ap.add_argument("--settle", type=float, default=1.0, help="seconds of extra warm-up load before timing")
     ap.add_argument("--ncu", action="store_true", help="3 warm-up steps + 1 eager step only (for ncu -s/-c)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every step eagerly (no CUDA graph replay)")
     args = ap.parse_args()

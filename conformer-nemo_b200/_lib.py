@@ -22,7 +22,7 @@ STATUS_NAMES = {1: "invalid argument", 2: "unsupported configuration", 3: "missi
 # every symbol include/cfb.h declares (tests check that the built library exports each of them)
 SYMBOLS = [
     "cfb_create", "cfb_destroy", "cfb_last_error", "cfb_set_weight", "cfb_finalize_weights", "cfb_output_frames",
-    "cfb_workspace_bytes", "cfb_forward", "cfb_debug_buffer", "cfb_set_profiling", "cfb_profile_report",
+    "cfb_workspace_bytes", "cfb_forward", "cfb_packed_workspace_bytes", "cfb_forward_packed", "cfb_debug_buffer", "cfb_set_profiling", "cfb_profile_report",
     "cfb_last_launch_count", "cfb_op_gemm", "cfb_op_gemm_ln", "cfb_op_gemm_lnt", "cfb_op_ctc_head", "cfb_ctc_head_scratch_bytes", "cfb_op_ctc_collapse",
     "cfb_op_layernorm", "cfb_op_depthwise", "cfb_op_dw_pw2", "cfb_op_logmel", "cfb_op_rel_attention", "cfb_op_lengths",
     "cfb_rnnt_greedy_scratch_bytes", "cfb_op_rnnt_greedy",
@@ -75,6 +75,8 @@ def load_library() -> ctypes.CDLL:
         lib.cfb_output_frames.argtypes = [vp, i32, ctypes.POINTER(i32)]
         lib.cfb_workspace_bytes.argtypes = [vp, i32, i32, ctypes.POINTER(sz)]
         lib.cfb_forward.argtypes = [vp, vp, i32, vp, i32, i32, vp, i32, vp, vp, sz, vp]
+        lib.cfb_packed_workspace_bytes.argtypes = [vp, vp, i32, i32, ctypes.POINTER(sz)]
+        lib.cfb_forward_packed.argtypes = [vp, vp, i32, vp, vp, i32, i32, vp, i32, vp, vp, sz, vp]
         lib.cfb_debug_buffer.argtypes = [vp, i32, i32, ctypes.c_char_p, ctypes.POINTER(sz), ctypes.POINTER(sz)]
         lib.cfb_last_launch_count.argtypes = [vp]
         lib.cfb_set_profiling.argtypes = [vp, i32]

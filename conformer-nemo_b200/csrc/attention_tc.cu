@@ -64,6 +64,7 @@ struct AttnParams {
   const int32_t* lens;
   bf16* ctx;
   int T, Dp;
+  const int4* tiles;  // packed batches: blockIdx.x -> (sequence, i0, first token row of its slot, rows in the slot)
   float scale_log2;  // log2(e) / sqrt(dk)
   int debug;         // CFB_ATTN_DEBUG ablation bits (timing experiments only; results are wrong when non-zero)
   long long* trace;  // CFB_ATTN_TRACE=1: clock64 trace of CTA (0,0,0) (timing experiments only)
@@ -98,10 +99,8 @@ template <bool kInstr>  // kInstr: clock trace + ablation switches (timing exper
 __global__ void __launch_bounds__(kThreads, 1)
 rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmP,
                    const AttnParams p) {
-  const int i0 = blockIdx.x * kBM;
   const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int T = p.T;
+  const int T = p.T;  // extent of the positional table (2T - 1 band rows)
   uint32_t tid;
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));  // volatile: keeps warp / lane in registers (no S2R re-reads)
   const int warp = tid >> 5;
@@ -167,7 +166,14 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   }
   pdl_launch_dependents();
   pdl_wait();
-  const int len = min(p.lens[b], T);
+  // dense layout: sequence b owns rows [b T, b T + T); packed: the slot [rb, rb + S) of the tile table
+  int i0 = blockIdx.x * kBM, b = blockIdx.z, S = T;
+  long long rb = static_cast<long long>(b) * T;
+  if (p.tiles != nullptr) {
+    const int4 t = __ldg(p.tiles + blockIdx.x);
+    b = t.x, i0 = t.y, rb = t.z, S = t.w;
+  }
+  const int len = min(p.lens[b], S);
   const bool active = i0 < len;  // otherwise the whole query tile is padding: the context rows are zero
   const int n_kt = active ? (len + kBN - 1) / kBN : 0;
   const int n_gb = n_kt + 2;  // G blocks 0 .. n_kt+1
@@ -175,8 +181,8 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   uint32_t qw[32];  // softmax warps: this thread's row of Q+u (set 0) / Q+v (set 1), 64 bf16, fetched before the setup
   if (warp >= 4 && active) {
     const int i = i0 + (warp & 3) * 32 + lane;
-    if (i < T) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<long long>(b) * T + i) * (4 * p.Dp) +
+    if (i < S) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (rb + i) * (4 * p.Dp) +
                                                         ((warp - 4) >> 2) * p.Dp + h * kDK);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -198,8 +204,8 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       ptx::tma_load_2d_a(sbase + kOffBand + g * kBlockBytes, &tmP, band_full + 8 * g, h * kDK, r0 + 64 * g);
     }
     ptx::mbar_arrive_expect_tx_a(kv_full, kKVBytes);
-    ptx::tma_load_2d_a(sbase + kOffKV, &tmKV, kv_full, 2 * p.Dp + h * kDK, b * T);
-    ptx::tma_load_2d_a(sbase + kOffKV + kKBytes, &tmKV, kv_full, 3 * p.Dp + h * kDK, b * T);
+    ptx::tma_load_2d_a(sbase + kOffKV, &tmKV, kv_full, 2 * p.Dp + h * kDK, static_cast<int>(rb));
+    ptx::tma_load_2d_a(sbase + kOffKV + kKBytes, &tmKV, kv_full, 3 * p.Dp + h * kDK, static_cast<int>(rb));
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -211,8 +217,8 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   if (!active) {
     if (warp >= 4 && warp < 8) {
       const int i = i0 + (warp & 3) * 32 + lane;
-      if (i < T) {
-        uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(b) * T + i) * p.Dp + h * kDK);
+      if (i < S) {
+        uint4* o = reinterpret_cast<uint4*>(p.ctx + (rb + i) * p.Dp + h * kDK);
 #pragma unroll
         for (int c = 0; c < 8; ++c) o[c] = make_uint4(0, 0, 0, 0);
       }
@@ -236,8 +242,8 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
           ptx::mbar_wait_a(kv_empty + 8 * st, (use & 1) ^ 1);
           ptx::mbar_arrive_expect_tx_a(kv_full + 8 * st, kKVBytes);
           const uint32_t dst = sbase + kOffKV + st * kKVBytes;
-          ptx::tma_load_2d_a(dst, &tmKV, kv_full + 8 * st, 2 * p.Dp + h * kDK, b * T + kt * kBN);
-          ptx::tma_load_2d_a(dst + kKBytes, &tmKV, kv_full + 8 * st, 3 * p.Dp + h * kDK, b * T + kt * kBN);
+          ptx::tma_load_2d_a(dst, &tmKV, kv_full + 8 * st, 2 * p.Dp + h * kDK, static_cast<int>(rb) + kt * kBN);
+          ptx::tma_load_2d_a(dst + kKBytes, &tmKV, kv_full + 8 * st, 3 * p.Dp + h * kDK, static_cast<int>(rb) + kt * kBN);
           load_band_block(kt + 3);
         }
       }
@@ -516,8 +522,8 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       const float l = l_run * w0 + l1 * w1;
       const float inv = (i < len && l > 0.f) ? 1.f / l : 0.f;  // padded query rows -> zeros
       const float c0 = w0 * inv, c1 = w1 * inv;
-      if (i < T) {
-        uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(b) * T + i) * p.Dp + h * kDK);
+      if (i < S) {
+        uint4* o = reinterpret_cast<uint4*>(p.ctx + (rb + i) * p.Dp + h * kDK);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 x0 = lds_f32x4(xrow + 16 + 32 * c), x1 = lds_f32x4(xrow + 32 + 32 * c);
@@ -555,18 +561,20 @@ extern "C" __attribute__((visibility("default"))) int cfb_debug_attn_trace(long 
 }
 
 int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
-  if (a.B <= 0 || a.T <= 0) return 0;
+  if ((a.tiles == nullptr && a.B <= 0) || a.T <= 0) return 0;
   {
     // persistent form (attention_tcp.cu).  Measured (r02t): 256 x 100 frames x 4 heads 48.3 -> 43.3 us, 32 x 500 x 8
     // 93.3 -> 92.1 us, 1 x 7500 x 8 477 -> 504 us: it removes the per-CTA setup, which matters for short sequences; the
     // per-item time is set by the softmax warps' serial work either way.  CFB_ATTN_PERSIST=1 / 0 forces.
     const char* pv = getenv("CFB_ATTN_PERSIST");
     const bool instrumented = getenv("CFB_ATTN_TRACE") != nullptr || getenv("CFB_ATTN_DEBUG") != nullptr;
-    const bool want = pv != nullptr ? atoi(pv) != 0 : a.T <= 512;
+    // packed batches: the tiles of one launch differ widely in length, which the hardware's dynamic CTA scheduling
+    // absorbs and a static item walk does not -- per-item form unless forced
+    const bool want = pv != nullptr ? atoi(pv) != 0 : (a.tiles == nullptr && a.T <= 512);
     if (want && !instrumented) return launch_attn_tcp(a, st, err);
   }
   const int Dp = a.H * a.dkp;
-  const long long rows = static_cast<long long>(a.B) * a.T;
+  const long long rows = a.tiles != nullptr ? a.rows : static_cast<long long>(a.B) * a.T;
   CUtensorMap tmKV, tmP;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(4 * Dp), static_cast<uint64_t>(rows)};
@@ -600,6 +608,7 @@ int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
   p.ctx = reinterpret_cast<bf16*>(a.ctx);
   p.T = a.T;
   p.Dp = Dp;
+  p.tiles = a.tiles;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(a.dk));
   p.trace = nullptr;
   {
@@ -614,6 +623,7 @@ int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
     p.trace = g_attn_trace;
   }
   dim3 grid((a.T + kBM - 1) / kBM, a.H, a.B);
+  if (a.tiles != nullptr) grid = dim3(a.n_tiles, a.H, 1);
   cudaError_t e;
   if (p.trace != nullptr || p.debug != 0)
     e = launch_pdl(rel_attn_tc_kernel<true>, grid, dim3(kThreads), kSmemTotal, st, tmKV, tmP, p);

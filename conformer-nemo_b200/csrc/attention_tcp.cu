@@ -72,8 +72,9 @@ struct AttnPParams {
   const int32_t* lens;
   bf16* ctx;
   int T, Dp, H;
-  int n_qt;          // query tiles per sequence
+  int n_qt;          // query tiles per sequence (dense layout) / query tiles in the tile table (packed)
   int n_items;       // B * H * n_qt, query tile fastest (CTAs that share K / V / band rows run side by side)
+  const int4* tiles; // packed batches: (sequence, i0, first token row of the slot, rows in the slot); items = n_qt x H
   float scale_log2;  // log2(e) / sqrt(dk)
 };
 
@@ -176,16 +177,25 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
   // item -> (query tile, head, sequence) and the tile counts every role derives identically
   struct Item {
     int i0, h, b, len, n_kt, n_gb;
+    int rb, S;  // first token row and row count of the sequence (dense: b T and T; packed: its slot)
     bool active;
   };
   auto decode = [&](int item) {
     Item it;
     const int qt = item % p.n_qt;
     const int r = item / p.n_qt;
-    it.h = r % p.H;
-    it.b = r / p.H;
-    it.i0 = qt * kBM;
-    it.len = min(__ldg(p.lens + it.b), T);
+    if (p.tiles != nullptr) {
+      const int4 t = __ldg(p.tiles + qt);
+      it.h = r;
+      it.b = t.x, it.i0 = t.y, it.rb = t.z, it.S = t.w;
+    } else {
+      it.h = r % p.H;
+      it.b = r / p.H;
+      it.i0 = qt * kBM;
+      it.rb = it.b * T;
+      it.S = T;
+    }
+    it.len = min(__ldg(p.lens + it.b), it.S);
     it.active = it.i0 < it.len;  // otherwise the whole query tile is padding: the context rows are zero
     it.n_kt = it.active ? (it.len + kBN - 1) / kBN : 0;
     it.n_gb = it.active ? it.n_kt + 2 : 0;
@@ -222,8 +232,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
             ptx::mbar_wait_a(kv_empty + 8 * st, (use & 1) ^ 1);
             ptx::mbar_arrive_expect_tx_a(kv_full + 8 * st, kKVBytes);
             const uint32_t dst = sbase + kOffKV + st * kKVBytes;
-            ptx::tma_load_2d_a(dst, &tmKV, kv_full + 8 * st, 2 * p.Dp + w.h * kDK, w.b * T + kt * kBN);
-            ptx::tma_load_2d_a(dst + kKBytes, &tmKV, kv_full + 8 * st, 3 * p.Dp + w.h * kDK, w.b * T + kt * kBN);
+            ptx::tma_load_2d_a(dst, &tmKV, kv_full + 8 * st, 2 * p.Dp + w.h * kDK, w.rb + kt * kBN);
+            ptx::tma_load_2d_a(dst + kKBytes, &tmKV, kv_full + 8 * st, 3 * p.Dp + w.h * kDK, w.rb + kt * kBN);
           };
           load_band_block(0);
           load_band_block(1);
@@ -351,12 +361,11 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     // this thread's row of Q+u (set 0) / Q+v (set 1) of an item: 64 bf16
     uint32_t qw[32];
     auto fetch_q = [&](int item) {
-      const int qt = item % p.n_qt;
-      const int r = item / p.n_qt;
-      const int h = r % p.H, b = r / p.H;
-      const int i = qt * kBM + ii;
-      if (i < T) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<long long>(b) * T + i) * (4 * p.Dp) +
+      const Item f = decode(item);
+      const int h = f.h;
+      const int i = f.i0 + ii;
+      if (i < f.S) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (static_cast<long long>(f.rb) + i) * (4 * p.Dp) +
                                                           set * p.Dp + h * kDK);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -390,8 +399,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       const Item w = decode(item);
       const int i = w.i0 + ii;
       if (!w.active) {
-        if (set == 0 && i < T) {
-          uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(w.b) * T + i) * p.Dp + w.h * kDK);
+        if (set == 0 && i < w.S) {
+          uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(w.rb) + i) * p.Dp + w.h * kDK);
 #pragma unroll
           for (int c = 0; c < 8; ++c) o[c] = make_uint4(0, 0, 0, 0);
         }
@@ -531,8 +540,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         const float l = l_run * w0 + l1 * w1;
         const float inv = (i < len && l > 0.f) ? 1.f / l : 0.f;  // padded query rows -> zeros
         const float c0 = w0 * inv, c1 = w1 * inv;
-        if (i < T) {
-          uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(w.b) * T + i) * p.Dp + w.h * kDK);
+        if (i < w.S) {
+          uint4* o = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(w.rb) + i) * p.Dp + w.h * kDK);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 x0 = lds_f32x4(xrow + 16 + 32 * c), x1 = lds_f32x4(xrow + 32 + 32 * c);
@@ -561,13 +570,13 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
 }  // namespace
 
 int launch_attn_tcp(const AttnDesc& a, cudaStream_t st, std::string* err) {
-  if (a.B <= 0 || a.T <= 0) return 0;
+  if ((a.tiles == nullptr && a.B <= 0) || a.T <= 0) return 0;
   if (a.dkp != kDK) {
     if (err) *err = "attn_tcp: padded head dim must be 64";
     return -1;
   }
   const int Dp = a.H * a.dkp;
-  const long long rows = static_cast<long long>(a.B) * a.T;
+  const long long rows = a.tiles != nullptr ? a.rows : static_cast<long long>(a.B) * a.T;
   CUtensorMap tmKV, tmP;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(4 * Dp), static_cast<uint64_t>(rows)};
@@ -602,8 +611,9 @@ int launch_attn_tcp(const AttnDesc& a, cudaStream_t st, std::string* err) {
   p.T = a.T;
   p.Dp = Dp;
   p.H = a.H;
-  p.n_qt = (a.T + kBM - 1) / kBM;
-  p.n_items = a.B * a.H * p.n_qt;
+  p.n_qt = a.tiles != nullptr ? a.n_tiles : (a.T + kBM - 1) / kBM;
+  p.n_items = (a.tiles != nullptr ? 1 : a.B) * a.H * p.n_qt;
+  p.tiles = a.tiles;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(a.dk));
   const int grid = p.n_items < sms[dev & 63] ? p.n_items : sms[dev & 63];
   cudaError_t e = launch_pdl(rel_attn_tcp_kernel, dim3(grid), dim3(kThreads), kSmemTotal, st, tmKV, tmP, p);

@@ -22,6 +22,7 @@ struct EpiParams {
   float alpha = 1.f;             // RESID scale
   const int32_t* lens = nullptr; // GLU / LINEAR: valid frames per sequence (null = no masking)
   int frames_per_seq = 1;
+  const int32_t* row_t = nullptr; // packed batches: frame index of every output row, < 0 at gap rows (replaces lens)
   int qkv_dp = 0;                // QKV: H * dk_pad
   int M = 0;                     // valid output rows
   int N = 0;                     // accumulator columns
@@ -105,7 +106,40 @@ struct AttnDesc {
   void* ctx = nullptr;  // (B*T, Dp)
   const int32_t* lens = nullptr;
   int B = 0, T = 0, H = 0, dk = 0, dkp = 0;
+  // packed batches (PackedTables): qkv / ctx have `rows` token rows, every sequence owns a slot of them; T stays the
+  // extent of the positional table (the longest sequence).  tiles == nullptr: the dense (B, T) layout above.
+  const int4* tiles = nullptr;  // [n_tiles] (sequence, first query row i0, first token row of the slot, rows in the slot)
+  int n_tiles = 0;
+  long long rows = 0;
 };
+
+// ---- packed (variable-length) batches ---------------------------------------------------------------------------
+// Every utterance owns a SLOT of token rows: its T'_b valid frames followed by >= 15 gap rows (slot sizes are multiples
+// of 8), slots back to back.  Token-major kernels (LayerNorm, GEMMs) simply run over all rows; the depth-wise
+// convolution sees one long sequence whose gap rows are zero in its input (its 15-frame halo never reaches a
+// neighbour); attention works per slot; the strided convolutions run over the matching "virtual" time axis (4 input
+// frames / 2 first-conv rows per token row).  Tables are built on the device from the lengths (packed.cu).
+constexpr int kPackGap = 15;   // >= (31 - 1) / 2: the depth-wise halo
+constexpr int kPackAlign = 8;  // slot granularity in token rows (= 16 first-conv rows = one im2col block)
+struct PackedTables {
+  int32_t* seq_row0 = nullptr;  // [B] first token row of the slot
+  int32_t* seq_rows = nullptr;  // [B] token rows in the slot
+  int32_t* row_t = nullptr;     // [N] frame index inside the utterance, -1 at gap rows
+  int32_t* row_out = nullptr;   // [N] row of the dense (B, T2, d) result, -1 at gap rows
+  int32_t* blk_seq = nullptr;   // [N / 8] utterance owning every 8-row block
+  int4* tiles = nullptr;        // [n_tiles] attention query tiles (b, i0, row0, rows)
+};
+inline int packed_slot_rows(int t2) { return (t2 + kPackGap + kPackAlign - 1) / kPackAlign * kPackAlign; }
+// lengths: (B) int64 input frames on the device (clipped to [0, T]); T2 = dense output extent; n_rows / n_tiles as
+// computed by the host from the same lengths.  One CTA.
+int launch_packed_plan(const long long* lengths, int B, int T, int T2, int n_rows, int n_tiles, const PackedTables& tb,
+                       cudaStream_t st);
+// conv0_im2col for the packed layout: rows of slot b come from feats[b]; first-conv rows t1 > T1_b or >= T1 are zero
+int launch_conv0_im2col_packed(const void* feats, bool feats_bf16, const long long* lengths, void* a0, int B, int F, int T,
+                               int T1, int F1, int Fh, int n_rows, const PackedTables& tb, cudaStream_t st);
+// LayerNorm whose output rows are scattered through row_map (rows with a negative entry are skipped)
+int launch_layernorm_scatter(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int rows,
+                             int d, const int32_t* row_map, cudaStream_t st);
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
 // Every product-path kernel is launched with programmaticStreamSerialization: its CTAs may start (barrier init,

@@ -98,17 +98,47 @@ int conv_out(int n) { return (n - 1) / 2 + 1; }  // k=3, s=2, p=1 (n >= 1)
 struct Plan {
   int B, T, T1, T2, Th, N, P;  // P = 2*T2-1
   size_t y1, y2, x, a, hbuf, qkv, ctx, g, c, pe, pos, a0, raw, cols, total;
+  size_t tables;  // packed batches only: the PackedTables arrays
+  int n_tiles;
 };
 
-Plan make_plan(const cfb_handle* h, int B, int T) {
+// Layout of a packed batch, computed from host-side lengths with the integer arithmetic packed_plan_kernel uses.
+struct PackedShape {
+  int n_rows = 0;   // token rows over all slots
+  int n_tiles = 0;  // attention query tiles
+  int t2_max = 0;   // dense output extent T' of the padded batch
+};
+PackedShape packed_shape(const int64_t* lengths_host, int B, int T) {
+  PackedShape ps;
+  ps.t2_max = conv_out(conv_out(T));
+  for (int b = 0; b < B; ++b) {
+    long long len = lengths_host ? lengths_host[b] : T;
+    len = len < 0 ? 0 : (len > T ? T : len);
+    const int t1 = static_cast<int>((len + 1) >> 1);
+    const int t2 = (t1 + 1) >> 1;
+    const int rows = packed_slot_rows(t2);
+    ps.n_rows += rows;
+    ps.n_tiles += (rows + 127) / 128;
+  }
+  return ps;
+}
+
+// packed_rows > 0: one virtual sequence of 4 * packed_rows input frames (common.cuh, PackedTables) whose positional
+// table covers t2_pos frames; otherwise the dense (B, T) batch.
+Plan make_plan(const cfb_handle* h, int B, int T, int packed_rows = 0, int t2_pos = 0, int packed_B = 0, int n_tiles = 0) {
   Plan p{};
+  if (packed_rows > 0) {
+    B = 1;
+    T = 4 * packed_rows;
+  }
   p.B = B;
   p.T = T;
   p.T1 = conv_out(T);
   p.T2 = conv_out(p.T1);
   p.Th = (p.T1 + 1) / 2;
   p.N = B * p.T2;
-  p.P = 2 * p.T2 - 1;
+  p.P = 2 * (packed_rows > 0 ? t2_pos : p.T2) - 1;
+  p.n_tiles = n_tiles;
   const size_t e = h->esz();
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -139,8 +169,22 @@ Plan make_plan(const cfb_handle* h, int B, int T) {
     p.raw = take(raw * 4);
     p.cols = take(N * h->F2 * 9 * h->C * 4);
   }
+  if (packed_rows > 0)
+    p.tables = take((static_cast<size_t>(2) * packed_B + 2 * N + N / kPackAlign + 8) * 4 + static_cast<size_t>(n_tiles) * 16 + 64);
   p.total = off;
   return p;
+}
+
+PackedTables carve_tables(uint8_t* base, int B, int n_rows) {
+  PackedTables t;
+  int32_t* q = reinterpret_cast<int32_t*>(base);
+  t.seq_row0 = q, q += B;
+  t.seq_rows = q, q += B;
+  t.row_t = q, q += n_rows;
+  t.row_out = q, q += n_rows;
+  t.blk_seq = q, q += n_rows / kPackAlign;
+  t.tiles = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(q) + 15) & ~uintptr_t(15));
+  return t;
 }
 
 // cfb_forward may run a batch as two half-batches on two streams, each half with its own plan
@@ -616,15 +660,19 @@ int cfb_debug_buffer(const cfb_handle* h, int B, int T, const char* name, size_t
 }  // extern "C"
 
 // One contiguous range of the batch on one stream (the whole batch, or one half of it).
+// pk != nullptr: the batch runs in the packed layout (every utterance in its own slot of token rows, no padding).
 static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, const int64_t* lengths, int B, int T,
                          void* encoded, int out_dtype, int32_t* encoded_len, void* workspace, cudaStream_t st,
-                         int* launches_out, int B_total) {
-  const Plan pl = make_plan(h, B, T);
+                         int* launches_out, int B_total, const PackedShape* pk = nullptr) {
+  const Plan pl = pk ? make_plan(h, B, T, pk->n_rows, pk->t2_max, B, pk->n_tiles) : make_plan(h, B, T);
+  const int Bk = pk ? 1 : B;  // batch extent the kernels see: a packed batch is one long sequence
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const bool v = h->validate;
   const bool abf = !v;  // activations / matrices in bf16
   const int d = h->d, C = h->C, F2 = h->F2, dff = h->dff, H = h->H, Dp = h->Dp, L = h->L;
   const int N = pl.N, T2 = pl.T2;
+  PackedTables tb;
+  if (pk) tb = carve_tables(reinterpret_cast<uint8_t*>(workspace) + pl.tables, B, pk->n_rows);
   std::string err;
   int launches = 0;
   float* raw = v ? reinterpret_cast<float*>(ws + pl.raw) : nullptr;
@@ -689,7 +737,7 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
   // Row-complete GEMM with the residual update and the following LayerNorm(s) in its epilogue (gemm_ln.cu): the
   // product path for d_model <= 512.  ln1 / ln2 index lw.ln_g / lw.ln_b of the given layers (-1 = none).
   static const bool fused_env = getenv("CFB_FUSED_LN") != nullptr && atoi(getenv("CFB_FUSED_LN")) != 0;
-  const bool fused_ln = fused_env && !v && d <= 512;
+  const bool fused_ln = fused_env && !v && d <= 512 && !pk;
   // conv-module tail as one kernel (conv_tail.cu) whenever the shape allows it; CFB_FUSED_TAIL=0 keeps the two launches
   const char* tail_var = getenv("CFB_FUSED_TAIL");  // 0 = never, 2 = whenever the shape allows, unset = heuristic
   const bool tail_env = !(tail_var != nullptr && atoi(tail_var) == 0);
@@ -701,7 +749,7 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     if (sms <= 0) sms = 148;
-    const long long ctas = static_cast<long long>(B_total) * ((T2 + 127) / 128);
+    const long long ctas = static_cast<long long>(pk ? 1 : B_total) * ((T2 + 127) / 128);
     const long long waves = (ctas + sms - 1) / sms;
     fused_tail = ctas * 100 >= waves * sms * 65;
   }  // experimental: measured slower than GEMM + LayerNorm (gemm_ln.cu)
@@ -743,16 +791,27 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
   // ---- lengths (subsampling.py:164-171)
   CFB_TRY(launch_lengths(reinterpret_cast<const long long*>(lengths), encoded_len, B, T, 2, st), "lengths");
   ++launches;
+  if (pk) {
+    CFB_TRY(launch_packed_plan(reinterpret_cast<const long long*>(lengths), B, T, pk->t2_max, pk->n_rows, pk->n_tiles, tb, st),
+            "packed layout tables");
+    ++launches;
+  }
   // ---- subsampling: conv 1->C, conv C->C, linear (subsampling.py:172-175)
   const char* c0_var = getenv("CFB_CONV0_GEMM");  // 0 = CUDA-core kernel; default: patch gather + tcgen05 GEMM
-  if (!v && !(c0_var != nullptr && atoi(c0_var) == 0)) {
-    CFB_TRY(launch_conv0_im2col(feats, feats_dtype == CFB_BF16, ws + pl.a0, B, h->F0, T, pl.T1, h->F1, pl.Th, h->Fh, st),
-            "subsample conv 0 (gather)");
+  if (pk || (!v && !(c0_var != nullptr && atoi(c0_var) == 0))) {
+    if (pk) {
+      CFB_TRY(launch_conv0_im2col_packed(feats, feats_dtype == CFB_BF16, reinterpret_cast<const long long*>(lengths),
+                                         ws + pl.a0, B, h->F0, T, conv_out(T), h->F1, h->Fh, pk->n_rows, tb, st),
+              "subsample conv 0 (gather)");
+    } else {
+      CFB_TRY(launch_conv0_im2col(feats, feats_dtype == CFB_BF16, ws + pl.a0, B, h->F0, T, pl.T1, h->F1, pl.Th, h->Fh, st),
+              "subsample conv 0 (gather)");
+    }
     ++launches;
     EpiParams ep;
     ep.out = ws + pl.y1;
     ep.ldo = C;
-    CFB_TRY(gemm(ws + pl.a0, kConv0Cols, h->sub_w1g, kConv0Cols, B * 4 * pl.Th * h->Fh, C, kConv0Cols, EPI_RELU, true, ep,
+    CFB_TRY(gemm(ws + pl.a0, kConv0Cols, h->sub_w1g, kConv0Cols, Bk * 4 * pl.Th * h->Fh, C, kConv0Cols, EPI_RELU, true, ep,
                  "subsample conv 0"),
             "subsample conv 0");
   } else {
@@ -778,7 +837,7 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     cd.W = h->arena + h->sub_w2.off;
     cd.bias = h->at<float>(h->sub_b2);
     cd.y_out = ws + pl.y2;
-    cd.B = B;
+    cd.B = Bk;
     cd.C_in = C;
     cd.C_out = C;
     cd.Th = pl.Th;
@@ -803,7 +862,8 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
             "pre_encode.out");
   }
   // ---- relative positional table and its per-layer projections (multi_head_attention.py:186-188, 296-316)
-  CFB_TRY(launch_pos_table(ws + pl.pe, abf, h->at<float>(h->div_term), T2, d, st), "pos table");
+  const int T2pos = pk ? pk->t2_max : T2;  // extent of the relative-position table
+  CFB_TRY(launch_pos_table(ws + pl.pe, abf, h->at<float>(h->div_term), T2pos, d, st), "pos table");
   ++launches;
   {
     EpiParams ep;
@@ -915,10 +975,15 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
         ad.ctx = ws + pl.ctx;
         ad.lens = lens;
         ad.B = B;
-        ad.T = T2;
+        ad.T = T2pos;
         ad.H = H;
         ad.dk = h->dk;
         ad.dkp = h->dkp;
+        if (pk) {
+          ad.tiles = tb.tiles;
+          ad.n_tiles = pk->n_tiles;
+          ad.rows = N;
+        }
         CFB_TRY(v ? launch_attn_simt(ad, st, &err) : launch_attn_tc(ad, st, &err), "rel-pos attention");
         ++launches;
         EpiParams eo;
@@ -935,8 +1000,12 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
         eg.bias = h->at<float>(lw.b_pw1);
         eg.out = ws + pl.g;
         eg.ldo = d;
-        eg.lens = lens;
-        eg.frames_per_seq = T2;
+        if (pk) {
+          eg.row_t = tb.row_t;  // zero at the gap rows: the depth-wise halo of a slot must not see its neighbours
+        } else {
+          eg.lens = lens;
+          eg.frames_per_seq = T2;
+        }
         CFB_TRY(gemm(a, d, lw.w_pw1, d, N, 2 * d, d, EPI_GLU, abf, eg, "pointwise_conv1+glu"), "pointwise_conv1+glu");
         if (fused_tail) {
           // depthwise + BatchNorm + Swish + pointwise_conv2 + residual in one kernel (conv_tail.cu)
@@ -946,13 +1015,13 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
           dp.W = h->arena + lw.w_pw2.off;
           dp.bias2 = h->at<float>(lw.b_pw2);
           dp.x = x;
-          dp.B = B;
+          dp.B = Bk;
           dp.T = T2;
           dp.d = d;
           CFB_TRY(launch_dw_pw(dp, st, &err), "depthwise+pointwise_conv2");
           ++launches;
         } else {
-        CFB_TRY(launch_depthwise(ws + pl.g, h->at<float>(lw.dw_taps), h->at<float>(lw.dw_bias), ws + pl.c, abf, B, T2,
+        CFB_TRY(launch_depthwise(ws + pl.g, h->at<float>(lw.dw_taps), h->at<float>(lw.dw_bias), ws + pl.c, abf, Bk, T2,
                                  d, h->ksize, st),
                 "depthwise conv");
         ++launches;
@@ -984,7 +1053,14 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     }
     // -- norm_out (conformer_modules.py:120); the last one writes the result
     const bool last = (l == L - 1);
-    if (last && !h->has_out_proj) {
+    if (last && pk) {
+      // the dense (B, T', d) result of the reference API: zeros, then the valid rows of every slot (packed.cu)
+      const size_t out_bytes = static_cast<size_t>(B) * pk->t2_max * d * (out_dtype == CFB_BF16 ? 2 : 4);
+      if (cudaMemsetAsync(encoded, 0, out_bytes, st) != cudaSuccess) return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: memset failed");
+      CFB_TRY(launch_layernorm_scatter(x, h->at<float>(lw.ln_g[4]), h->at<float>(lw.ln_b[4]), encoded, out_dtype == CFB_BF16,
+                                       N, d, tb.row_out, st),
+              "norm_out");
+    } else if (last && !h->has_out_proj) {
       CFB_TRY(launch_layernorm(x, h->at<float>(lw.ln_g[4]), h->at<float>(lw.ln_b[4]), encoded, out_dtype == CFB_BF16, N,
                                d, lens, T2, st),
               "norm_out");
@@ -1059,6 +1135,39 @@ int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t
   cudaStreamWaitEvent(st, h->ev_join, 0);
   h->launches = launches;
   return rc != CFB_OK ? rc : rc1;
+}
+
+int cfb_packed_workspace_bytes(const cfb_handle* h, const int64_t* lengths_host, int B, int T, size_t* out) {
+  if (!h || !out || B < 1 || T < 1) return fail(h, CFB_ERR_INVALID_ARG, "cfb_packed_workspace_bytes: bad argument");
+  const PackedShape ps = packed_shape(lengths_host, B, T);
+  *out = make_plan(h, B, T, ps.n_rows, ps.t2_max, B, ps.n_tiles).total;
+  return CFB_OK;
+}
+
+int cfb_forward_packed(cfb_handle* h, const void* feats, int feats_dtype, const int64_t* lengths, const int64_t* lengths_host,
+                       int B, int T, void* encoded, int out_dtype, int32_t* encoded_len, void* workspace, size_t ws_bytes,
+                       cfb_stream stream) {
+  if (!h) return CFB_ERR_INVALID_ARG;
+  if (!h->finalized) return fail(h, CFB_ERR_STATE, "cfb_forward_packed: weights are not finalized");
+  if (!feats || !encoded || !encoded_len || !workspace || B < 1 || T < 1)
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward_packed: null pointer or empty batch");
+  if ((lengths == nullptr) != (lengths_host == nullptr))
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward_packed: lengths and lengths_host must both be given (or both NULL)");
+  if (feats_dtype != CFB_F32 && feats_dtype != CFB_BF16)
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward_packed: feats must be f32 or bf16");
+  if (out_dtype != CFB_F32 && out_dtype != CFB_BF16)
+    return fail(h, CFB_ERR_INVALID_ARG, "cfb_forward_packed: encoded must be f32 or bf16");
+  if (h->validate) return fail(h, CFB_ERR_UNSUPPORTED, "cfb_forward_packed: the fp32 validation path runs dense batches only");
+  if (h->has_out_proj) return fail(h, CFB_ERR_UNSUPPORTED, "cfb_forward_packed: out_proj (feat_out != d_model) runs dense batches only");
+  if (B > 2048) return fail(h, CFB_ERR_UNSUPPORTED, "cfb_forward_packed: at most 2048 utterances per call");
+  const PackedShape ps = packed_shape(lengths_host, B, T);
+  if (ws_bytes < make_plan(h, B, T, ps.n_rows, ps.t2_max, B, ps.n_tiles).total || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return fail(h, CFB_ERR_WORKSPACE, "cfb_forward_packed: workspace too small or not 256-byte aligned");
+  int launches = 0;
+  int rc = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, workspace,
+                         reinterpret_cast<cudaStream_t>(stream), &launches, B, &ps);
+  h->launches = launches;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

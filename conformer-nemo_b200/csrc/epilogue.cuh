@@ -125,7 +125,9 @@ template <int EPI, bool kFast>
 __device__ __forceinline__ void epi_math(const EpiParams& p, long long out_row, float (&acc)[32], const float (&b)[32]) {
   bool keep = true;
   if constexpr (EPI == EPI_LINEAR || EPI == EPI_SWISH || EPI == EPI_RELU || EPI == EPI_GLU) {
-    if (p.lens != nullptr) {
+    if (p.row_t != nullptr) {
+      keep = p.row_t[out_row] >= 0;
+    } else if (p.lens != nullptr) {
       const int seq = static_cast<int>(out_row / p.frames_per_seq);
       const int t = static_cast<int>(out_row - static_cast<long long>(seq) * p.frames_per_seq);
       keep = t < p.lens[seq];

@@ -175,6 +175,9 @@ class ConformerEncoder(nn.Module):
         self._use_graphs = False   # enable_cuda_graphs(): replay one captured graph per input shape
         self._graphs = OrderedDict()
         self._profiling = False
+        # "auto": mixed-length batches whose lengths are known on the host run in the packed layout (cfb_forward_packed)
+        # when that saves >= 15 % of the token rows; True / False force it on (whenever host lengths exist) / off
+        self.packed = "auto"
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.mark_weights_dirty())
         self.eval()
 
@@ -240,10 +243,10 @@ class ConformerEncoder(nn.Module):
         idle and its ~250 dependent launches are latency-bound, so overlapping sub-batches hides both.  Needs
         ``enable_cuda_graphs(True, private_workspaces=True)``; otherwise (or for a single sub-batch) runs them one after
         the other.  Returns ``[(encoded, encoded_len), ...]``; the caller's current stream waits for all of them."""
-        batches = list(batches)
+        batches = [tuple(bt) + (None,) * (3 - len(bt)) for bt in batches]  # (audio_signal, length[, length_host])
         if len(batches) <= 1 or n_streams <= 1 or self._profiling or \
                 not (self._use_graphs and getattr(self, "_graph_private_ws", False)):
-            return [self.forward(audio_signal=x, length=ln) for x, ln in batches]
+            return [self.forward(audio_signal=x, length=ln, length_host=hl) for x, ln, hl in batches]
         device = batches[0][0].device
         cur = torch.cuda.current_stream(device)
         pool = self.__dict__.setdefault("_side_streams", [])
@@ -252,8 +255,15 @@ class ConformerEncoder(nn.Module):
         fork = torch.cuda.Event()
         fork.record(cur)
         outs, owner = [], {}
-        for i, (x, ln) in enumerate(batches):
-            key = (tuple(x.shape), x.dtype, ln is not None)
+        for i, (x, ln, hl) in enumerate(batches):
+            # the identity _forward_graph gives the captured forward (same dtype normalisation, same packed decision):
+            # two sub-batches with equal keys share one graph and its static buffers, so they must stay on one stream
+            in_dtype = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32
+            host = hl if hl is not None else (ln.tolist() if ln is not None and not ln.is_cuda else None)
+            host = tuple(int(v) for v in (host.tolist() if torch.is_tensor(host) else host)) if host is not None else None
+            if not self._want_packed(host, x.shape[0], x.shape[2], self.output_frames(x.shape[2])):
+                host = None
+            key = self.graph_key(x.shape[0], x.shape[2], in_dtype, ln is not None, torch.float32, device.index, host)
             if key in owner:  # same shape = same graph and static buffers: keep stream order, detach the earlier result
                 k, j = owner[key]
                 with torch.cuda.stream(pool[k]):
@@ -264,7 +274,7 @@ class ConformerEncoder(nn.Module):
             if not any(o[0] == k for o in owner.values()):
                 stream.wait_event(fork)
             with torch.cuda.stream(stream):
-                outs.append(self.forward(audio_signal=x, length=ln))
+                outs.append(self.forward(audio_signal=x, length=ln, length_host=hl))
             owner[key] = (k, i)
         for k in {o[0] for o in owner.values()}:
             cur.wait_stream(pool[k])
@@ -348,15 +358,35 @@ class ConformerEncoder(nn.Module):
         return ws
 
     def forward(self, audio_signal: torch.Tensor, length: Optional[torch.Tensor] = None,
-                out_dtype: torch.dtype = torch.float32) -> Tuple[torch.Tensor, torch.Tensor]:
+                out_dtype: torch.dtype = torch.float32, length_host=None) -> Tuple[torch.Tensor, torch.Tensor]:
         """audio_signal (B, feat_in, T) float, length (B,) int or None -> (encoded (B, d_out, T'), encoded_len (B,)
         int32).  ``encoded`` is the transposed view of a contiguous (B, T', d_out) buffer, like the reference's
-        (conformer_encoder.py:280).  ``length=None`` means every row is T frames long (conformer_encoder.py:243-246)."""
+        (conformer_encoder.py:280).  ``length=None`` means every row is T frames long (conformer_encoder.py:243-246).
+        ``length_host`` (not in the reference): the same lengths as a host sequence / CPU tensor.  With it (or with a
+        CPU ``length``) a mixed-length batch runs in the packed layout -- same result bit for bit, no arithmetic on
+        padding (``self.packed``); without it the dense path runs and nothing synchronises with the host."""
         self.update_max_seq_length(seq_length=audio_signal.size(2), device=audio_signal.device)
-        return self.forward_for_export(audio_signal=audio_signal, length=length, out_dtype=out_dtype)
+        return self.forward_for_export(audio_signal=audio_signal, length=length, out_dtype=out_dtype,
+                                       length_host=length_host)
+
+    def packed_rows(self, lengths, t: int) -> int:
+        """Token rows of the packed layout for these input lengths (csrc/common.cuh: packed_slot_rows)."""
+        rows = 0
+        for n in lengths:
+            n = min(max(int(n), 0), t)
+            t2 = (((n + 1) >> 1) + 1) >> 1
+            rows += (t2 + 15 + 7) // 8 * 8
+        return rows
+
+    def _want_packed(self, host_lens, b, t, t_out) -> bool:
+        if host_lens is None or self.packed is False or self.precision != "bf16" or self.out_proj is not None or b > 2048:
+            return False
+        if self.packed is True:
+            return True
+        return self.packed_rows(host_lens, t) <= 0.85 * b * t_out
 
     @torch.no_grad()
-    def forward_for_export(self, audio_signal, length=None, out_dtype: torch.dtype = torch.float32):
+    def forward_for_export(self, audio_signal, length=None, out_dtype: torch.dtype = torch.float32, length_host=None):
         if audio_signal.dim() != 3 or audio_signal.size(1) != self._feat_in:
             raise TypeError(f"audio_signal must be (B, {self._feat_in}, T), got {tuple(audio_signal.shape)}")
         if not audio_signal.is_cuda:
@@ -376,30 +406,56 @@ class ConformerEncoder(nn.Module):
         if audio_signal.dtype not in (torch.float32, torch.bfloat16):
             audio_signal = audio_signal.float()
         feats = audio_signal.contiguous()
+        host_lens = None
         if length is not None:
             if length.dim() != 1 or length.numel() != b:
                 raise TypeError(f"length must have shape ({b},), got {tuple(length.shape)}")
+            if length_host is not None:
+                host_lens = tuple(int(v) for v in (length_host.tolist() if torch.is_tensor(length_host) else length_host))
+                if len(host_lens) != b:
+                    raise TypeError(f"length_host must have {b} entries")
+            elif not length.is_cuda:
+                host_lens = tuple(int(v) for v in length.tolist())
             length = length.to(device=device, dtype=torch.int64).contiguous()
         t_out = self.output_frames(t)
+        if not self._want_packed(host_lens, b, t, t_out):
+            host_lens = None  # dense path
         if self._use_graphs and not self._profiling and not torch.cuda.is_current_stream_capturing():
-            return self._forward_graph(feats, length, out_dtype, b, t, t_out, device)
+            return self._forward_graph(feats, length, out_dtype, b, t, t_out, device, host_lens)
         encoded = torch.empty(b, t_out, self._feat_out, dtype=out_dtype, device=device)
         encoded_len = torch.empty(b, dtype=torch.int32, device=device)
         nbytes = ctypes.c_size_t()
-        _lib.check(lib.cfb_workspace_bytes(self._handle, b, t, ctypes.byref(nbytes)), self._handle, "cfb_workspace_bytes")
+        if host_lens is not None:
+            hl = (ctypes.c_int64 * b)(*host_lens)
+            _lib.check(lib.cfb_packed_workspace_bytes(self._handle, hl, b, t, ctypes.byref(nbytes)), self._handle,
+                       "cfb_packed_workspace_bytes")
+        else:
+            _lib.check(lib.cfb_workspace_bytes(self._handle, b, t, ctypes.byref(nbytes)), self._handle, "cfb_workspace_bytes")
         ws = self._ensure_workspace(nbytes.value + 256, device)
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
-            _lib.check(lib.cfb_forward(
-                self._handle, ctypes.c_void_p(feats.data_ptr()), _DTYPES[feats.dtype],
-                ctypes.c_void_p(length.data_ptr()) if length is not None else None, b, t,
-                ctypes.c_void_p(encoded.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(encoded_len.data_ptr()),
-                ctypes.c_void_p(ws_ptr), nbytes.value, ctypes.c_void_p(stream)), self._handle, "cfb_forward")
+            if host_lens is not None:
+                _lib.check(lib.cfb_forward_packed(
+                    self._handle, ctypes.c_void_p(feats.data_ptr()), _DTYPES[feats.dtype],
+                    ctypes.c_void_p(length.data_ptr()), hl, b, t,
+                    ctypes.c_void_p(encoded.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(encoded_len.data_ptr()),
+                    ctypes.c_void_p(ws_ptr), nbytes.value, ctypes.c_void_p(stream)), self._handle, "cfb_forward_packed")
+            else:
+                _lib.check(lib.cfb_forward(
+                    self._handle, ctypes.c_void_p(feats.data_ptr()), _DTYPES[feats.dtype],
+                    ctypes.c_void_p(length.data_ptr()) if length is not None else None, b, t,
+                    ctypes.c_void_p(encoded.data_ptr()), _DTYPES[out_dtype], ctypes.c_void_p(encoded_len.data_ptr()),
+                    ctypes.c_void_p(ws_ptr), nbytes.value, ctypes.c_void_p(stream)), self._handle, "cfb_forward")
         return encoded.transpose(1, 2), encoded_len
 
-    def _forward_graph(self, feats, length, out_dtype, b, t, t_out, device):
-        key = (b, t, feats.dtype, length is not None, out_dtype, device.index)
+    @staticmethod
+    def graph_key(b, t, in_dtype, has_len, out_dtype, device_index, host_lens=None):
+        """Identity of a captured forward: a packed graph bakes the slot layout in, so it also depends on the lengths."""
+        return (b, t, in_dtype, has_len, out_dtype, device_index, host_lens)
+
+    def _forward_graph(self, feats, length, out_dtype, b, t, t_out, device, host_lens=None):
+        key = self.graph_key(b, t, feats.dtype, length is not None, out_dtype, device.index, host_lens)
         entry = self._graphs.get(key)
         if entry is None:
             if getattr(self, "_graph_private_ws", False):
@@ -414,11 +470,11 @@ class ConformerEncoder(nn.Module):
                 side = torch.cuda.Stream(device=device)
                 side.wait_stream(torch.cuda.current_stream(device))
                 with torch.cuda.stream(side):  # warm-up outside capture (workspace allocation, lazy module loading)
-                    self.forward_for_export(static_feats, static_len, out_dtype)
+                    self.forward_for_export(static_feats, static_len, out_dtype, length_host=host_lens)
                 torch.cuda.current_stream(device).wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    enc_t, enc_len = self.forward_for_export(static_feats, static_len, out_dtype)
+                    enc_t, enc_len = self.forward_for_export(static_feats, static_len, out_dtype, length_host=host_lens)
             finally:
                 self._use_graphs = True
             # the entry keeps the workspace the graph was captured with alive

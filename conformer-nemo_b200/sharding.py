@@ -109,11 +109,14 @@ def plan_shards(lengths: Sequence[int], n_ranks: int, max_batch: int = 64, bucke
 
 def forward_sharded(encode: Callable[[torch.Tensor, torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
                     features: Sequence[torch.Tensor], plan: ShardPlan, rank: int,
-                    device=None) -> Dict[int, Tuple[torch.Tensor, int]]:
+                    device=None, n_streams: int = 3) -> Dict[int, Tuple[torch.Tensor, int]]:
     """Runs rank ``rank``'s sub-batches.  ``features[i]`` is utterance i as a (feat_in, len_i) host tensor.
     Returns {utterance index: (encoded (d_out, T'_i) on the host, T'_i)} -- per-rank outputs go back to the host,
-    nothing is exchanged between ranks."""
+    nothing is exchanged between ranks.  ``encode`` is any ``(audio_signal, length) -> (encoded, encoded_len)`` callable;
+    a ``ConformerEncoder`` also receives the lengths as host values (so ragged sub-batches run in its packed layout) and
+    runs the rank's sub-batches through ``forward_many`` (concurrently when its CUDA graphs own their workspaces)."""
     results: Dict[int, Tuple[torch.Tensor, int]] = {}
+    staged = []
     for sub in plan.batches[rank]:
         lens = [int(features[i].shape[1]) for i in sub]
         t_max = max(lens)
@@ -124,7 +127,12 @@ def forward_sharded(encode: Callable[[torch.Tensor, torch.Tensor], Tuple[torch.T
         if device is not None:
             batch = batch.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else batch.to(device)
             length = length.to(device)
-        encoded, enc_len = encode(batch, length)
+        staged.append((sub, batch, length, lens))
+    if hasattr(encode, "forward_many"):
+        outs = encode.forward_many([(batch, length, lens) for _, batch, length, lens in staged], n_streams)
+    else:
+        outs = [encode(batch, length) for _, batch, length, _ in staged]
+    for (sub, _, _, _), (encoded, enc_len) in zip(staged, outs):
         encoded = encoded.detach().to("cpu")
         enc_len = enc_len.detach().to("cpu")
         for row, i in enumerate(sub):

@@ -109,6 +109,22 @@ CFB_API int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const
                 void* encoded, int out_dtype, int32_t* encoded_len, void* workspace, size_t ws_bytes,
                 cfb_stream stream);
 
+/* Variable-length ("packed") form of cfb_forward: same inputs, same outputs, and bit-identical results on every
+ * frame t < encoded_len[b] (frames behind it are zeros, as in cfb_forward) -- but no arithmetic is spent on padding.
+ * Each utterance occupies its own slot of token rows (its T'_b frames + a >= 15-row gap), so LayerNorm / GEMM kernels run
+ * over sum_b T'_b rows instead of B * T'max, attention works per slot, and the strided convolutions reproduce the
+ * reference's padded-batch edge effect (subsampling.py:172-175 runs them over the padded batch: the frame behind a short
+ * utterance is conv(zero-extended input), the one behind the longest is the convolution's zero padding).  This is what
+ * a length-bucketed shard of a mixed-length batch runs (the reference pads: audio_to_text.py:48-99).
+ *   lengths       (B,) int64 on the DEVICE (or NULL = all rows T long), as for cfb_forward
+ *   lengths_host  the same values in HOST memory: sizes the grids and the workspace; read during the call only
+ * Enqueue-only like cfb_forward (no allocation, no synchronisation, capturable: a captured graph is valid for these
+ * lengths).  CFB_ERR_UNSUPPORTED for the fp32 validation precision and for encoders with out_proj. */
+CFB_API int cfb_packed_workspace_bytes(const cfb_handle* h, const int64_t* lengths_host, int B, int T, size_t* out);
+CFB_API int cfb_forward_packed(cfb_handle* h, const void* feats, int feats_dtype, const int64_t* lengths,
+                       const int64_t* lengths_host, int B, int T, void* encoded, int out_dtype, int32_t* encoded_len,
+                       void* workspace, size_t ws_bytes, cfb_stream stream);
+
 /* Where an intermediate lives inside the workspace of a (B, T) forward (tests / debugging): name is one of
  * "y1" "y2" "x" "a" "h" "qkv" "ctx" "g" "c" "pe" "pos".  Offsets are bytes from the workspace base. */
 CFB_API int cfb_debug_buffer(const cfb_handle* h, int B, int T, const char* name, size_t* offset, size_t* bytes);

@@ -1,8 +1,9 @@
-"""Loads the UNMODIFIED reference ConformerEncoder from /root/reference -- TEST INFRASTRUCTURE ONLY.
+"""Loads the UNMODIFIED reference ConformerEncoder -- TEST INFRASTRUCTURE ONLY.
 
 Used in the build container to (a) generate the committed golden vectors (tests/golden/make_golden.py) and
-(b) cross-check oracle/conformer_oracle.py live when the reference tree is present.  It never runs on the
-GPU box (the reference tree does not travel) and nothing in the product imports it.
+(b) cross-check oracle/conformer_oracle.py live when the reference tree is present; on the GPU box, where
+/root/reference does not exist, the per-pod install under baseline/_ref (oracle/install_reference.py) lets
+bench.py's reference arm / cpu_baseline leg time the reference's own forward.  Nothing in the product imports it.
 
 ``import nemo.collections.asr`` fails here (hydra / sox / pytorch_lightning are not installed), so the five
 hot-path source files are imported directly after registering stub parent packages and no-op stand-ins for the
@@ -16,11 +17,26 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CONFORMER_REF", "/root/reference")
+_MARKER = "nemo/collections/asr/modules/conformer_encoder.py"
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root() -> str:
+    """Search order (GPU-box caveat): $CONFORMER_REF, the mounted tree, then the per-pod installs that
+    travel with the repository snapshot (baseline/_ref is written by oracle/install_reference.py, never committed)."""
+    cands = [os.environ.get("CONFORMER_REF"), "/root/reference", os.path.join(_REPO, "baseline", "_ref"),
+             os.path.join(_REPO, "oracle", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, _MARKER)):
+            return c
+    return os.environ.get("CONFORMER_REF") or "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "nemo/collections/asr/modules/conformer_encoder.py"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, _MARKER))
 
 
 def _stub_package(name: str, path: str) -> types.ModuleType:
