@@ -483,7 +483,14 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=device)
     kw = WORKLOADS[args.workload][0]
     enc = build_encoder(kw, device)
-    host_batches, audio_sec_job, scaling, extra_cfg = build_batches(args, kw, rank, world)
+    if args.share and world == 1:
+        # diagnostic: this one GPU runs the share rank R of a W-rank job would run (cfg3); `value` then counts the whole
+        # job's audio against this share's time, i.e. what the W-GPU job would report if R were its slowest rank
+        sr, sw = (int(v) for v in args.share.split("/"))
+        host_batches, audio_sec_job, scaling, extra_cfg = build_batches(args, kw, sr, sw)
+        extra_cfg = dict(extra_cfg or {}, emulated_share=f"rank {sr} of {sw} on one GPU")
+    else:
+        host_batches, audio_sec_job, scaling, extra_cfg = build_batches(args, kw, rank, world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -753,6 +760,7 @@ def main():
                     help="skip the cfg3 strong-scaling sub-record of the default (cfg2) line")
     ap.add_argument("--no-strong-sim", dest="strong_sim", action="store_false",
                     help="N=1: skip the one-GPU emulation of the 2/4/8-rank shares of cfg3")
+    ap.add_argument("--share", default="", help="cfg3 diagnostic on one GPU: R/W = run the share of rank R of a W-rank job")
     ap.add_argument("--settle", type=float, default=1.0, help="seconds of extra warm-up load before timing")
     ap.add_argument("--ncu", action="store_true", help="3 warm-up steps + 1 eager step only (for ncu -s/-c)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every step eagerly (no CUDA graph replay)")

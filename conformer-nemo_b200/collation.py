@@ -222,7 +222,10 @@ class CollationService:
         cols = max((self.lengths[i] for b in self.batches for i in b), default=0)
         self._use_cuda = self.device is not None and self.device.type == "cuda"
         pin = self._use_cuda and torch.cuda.is_available()
-        self._audio = [torch.empty(rows, cols, dtype=dtype, pin_memory=pin) for _ in range(self.depth)]
+        # flat slots: every sub-batch is collated into the CONTIGUOUS (n, max_len) prefix view of its slot, so the
+        # host-to-device copy is one cudaMemcpyAsync from pinned memory (a strided view of a (rows, cols) slot would make
+        # torch stage a pageable contiguous temporary first and copy synchronously)
+        self._audio = [torch.empty(rows * cols, dtype=dtype, pin_memory=pin) for _ in range(self.depth)]
         self._lens = [torch.empty(rows, dtype=torch.int64, pin_memory=pin) for _ in range(self.depth)]
         self._busy = [None] * self.depth  # event of the last copy out of each pinned slot
         self._stream = torch.cuda.Stream(self.device) if self._use_cuda else None
@@ -243,7 +246,8 @@ class CollationService:
             if sig.dim() != 1 or sig.numel() != self.lengths[i]:
                 raise ValueError(f"utterance {i}: load() returned {tuple(sig.shape)}, expected ({self.lengths[i]},)")
             items.append((sig.to(self.dtype), torch.tensor(sig.numel()), tok, torch.tensor(tok.numel()), self.sample_ids[i]))
-        return speech_collate(items, self.pad_id, audio_out=self._audio[slot])
+        n, max_len = len(idx), max(self.lengths[i] for i in idx)
+        return speech_collate(items, self.pad_id, audio_out=self._audio[slot][: n * max_len].view(n, max_len))
 
     def __iter__(self) -> Iterator[StagedBatch]:
         for n, idx in enumerate(self.batches):
@@ -257,7 +261,8 @@ class CollationService:
             ready = None
             if self._use_cuda:
                 with torch.cuda.stream(self._stream):
-                    audio = audio.to(self.device, non_blocking=True)  # strided (B, L) view of the slot: one 2-D copy
+                    assert audio.is_contiguous() and audio.is_pinned()  # one asynchronous copy straight from the slot
+                    audio = audio.to(self.device, non_blocking=True)
                     lens = lens.to(self.device, non_blocking=True)
                     ready = torch.cuda.Event()
                     ready.record(self._stream)

@@ -130,13 +130,15 @@ struct PackedTables {
   int4* tiles = nullptr;        // [n_tiles] attention query tiles (b, i0, row0, rows)
 };
 inline int packed_slot_rows(int t2) { return (t2 + kPackGap + kPackAlign - 1) / kPackAlign * kPackAlign; }
-// lengths: (B) int64 input frames on the device (clipped to [0, T]); T2 = dense output extent; n_rows / n_tiles as
-// computed by the host from the same lengths.  One CTA.
-int launch_packed_plan(const long long* lengths, int B, int T, int T2, int n_rows, int n_tiles, const PackedTables& tb,
-                       cudaStream_t st);
-// conv0_im2col for the packed layout: rows of slot b come from feats[b]; first-conv rows t1 > T1_b or >= T1 are zero
-int launch_conv0_im2col_packed(const void* feats, bool feats_bf16, const long long* lengths, void* a0, int B, int F, int T,
-                               int T1, int F1, int Fh, int n_rows, const PackedTables& tb, cudaStream_t st);
+// Lays out the group of B utterances first, first + step, ... of the batch.  lengths: int64 input frames of the WHOLE
+// batch on the device (clipped to [0, T]); T2 = dense output extent; n_rows / n_tiles as computed by the host from the
+// same lengths.  One CTA.
+int launch_packed_plan(const long long* lengths, int B, int first, int step, int T, int T2, int n_rows, int n_tiles,
+                       const PackedTables& tb, cudaStream_t st);
+// conv0_im2col for the packed layout: rows of slot k come from feats[first + k step]; first-conv rows t1 > T1_b or >= T1
+// are zero
+int launch_conv0_im2col_packed(const void* feats, bool feats_bf16, const long long* lengths, void* a0, int first, int step,
+                               int F, int T, int T1, int F1, int Fh, int n_rows, const PackedTables& tb, cudaStream_t st);
 // LayerNorm whose output rows are scattered through row_map (rows with a negative entry are skipped)
 int launch_layernorm_scatter(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int rows,
                              int d, const int32_t* row_map, cudaStream_t st);
@@ -153,6 +155,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 bool pdl_enabled();
+void set_pdl_auto(bool on);  // per host thread: the engine enables PDL for small batches (tmap.cu)
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include <cuda_fp16.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges are no-ops unless a profiler injected itself
 
 #include <algorithm>
 
@@ -107,11 +108,16 @@ struct PackedShape {
   int n_rows = 0;   // token rows over all slots
   int n_tiles = 0;  // attention query tiles
   int t2_max = 0;   // dense output extent T' of the padded batch
+  int first = 0, step = 1, count = 0;  // the group of utterances first, first + step, ... (count of them) this layout holds
+  bool prologue = true;  // this range also computes encoded_len and clears the dense result
 };
-PackedShape packed_shape(const int64_t* lengths_host, int B, int T) {
+PackedShape packed_shape(const int64_t* lengths_host, int B, int T, int first = 0, int step = 1) {
   PackedShape ps;
   ps.t2_max = conv_out(conv_out(T));
-  for (int b = 0; b < B; ++b) {
+  ps.first = first;
+  ps.step = step;
+  for (int b = first; b < B; b += step) {
+    ++ps.count;
     long long len = lengths_host ? lengths_host[b] : T;
     len = len < 0 ? 0 : (len > T ? T : len);
     const int t1 = static_cast<int>((len + 1) >> 1);
@@ -664,7 +670,7 @@ int cfb_debug_buffer(const cfb_handle* h, int B, int T, const char* name, size_t
 static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, const int64_t* lengths, int B, int T,
                          void* encoded, int out_dtype, int32_t* encoded_len, void* workspace, cudaStream_t st,
                          int* launches_out, int B_total, const PackedShape* pk = nullptr) {
-  const Plan pl = pk ? make_plan(h, B, T, pk->n_rows, pk->t2_max, B, pk->n_tiles) : make_plan(h, B, T);
+  const Plan pl = pk ? make_plan(h, B, T, pk->n_rows, pk->t2_max, pk->count, pk->n_tiles) : make_plan(h, B, T);
   const int Bk = pk ? 1 : B;  // batch extent the kernels see: a packed batch is one long sequence
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const bool v = h->validate;
@@ -672,7 +678,7 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
   const int d = h->d, C = h->C, F2 = h->F2, dff = h->dff, H = h->H, Dp = h->Dp, L = h->L;
   const int N = pl.N, T2 = pl.T2;
   PackedTables tb;
-  if (pk) tb = carve_tables(reinterpret_cast<uint8_t*>(workspace) + pl.tables, B, pk->n_rows);
+  if (pk) tb = carve_tables(reinterpret_cast<uint8_t*>(workspace) + pl.tables, pk->count, pk->n_rows);
   std::string err;
   int launches = 0;
   float* raw = v ? reinterpret_cast<float*>(ws + pl.raw) : nullptr;
@@ -680,7 +686,9 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
   // profiling: tick(label) before a launch group, tock() after it (CUDA events on the forward's stream)
   size_t prof_e0 = 0;
   const char* prof_label = nullptr;
+  // NVTX: one range per launch group, named like the profile report's labels (nsys / ncu --nvtx group kernels by them)
   auto tick = [&](const char* label) {
+    nvtxRangePushA(label);
     if (!h->profiling) return;
     if (h->ev_used + 2 > h->ev_pool.size()) {
       prof_label = nullptr;
@@ -691,6 +699,7 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     cudaEventRecord(h->ev_pool[prof_e0], st);
   };
   auto tock = [&]() {
+    nvtxRangePop();
     if (!h->profiling || !prof_label) return;
     const size_t e1 = h->ev_used++;
     cudaEventRecord(h->ev_pool[e1], st);
@@ -789,10 +798,13 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
   };
 
   // ---- lengths (subsampling.py:164-171)
-  CFB_TRY(launch_lengths(reinterpret_cast<const long long*>(lengths), encoded_len, B, T, 2, st), "lengths");
-  ++launches;
+  if (!pk || pk->prologue) {
+    CFB_TRY(launch_lengths(reinterpret_cast<const long long*>(lengths), encoded_len, B, T, 2, st), "lengths");
+    ++launches;
+  }
   if (pk) {
-    CFB_TRY(launch_packed_plan(reinterpret_cast<const long long*>(lengths), B, T, pk->t2_max, pk->n_rows, pk->n_tiles, tb, st),
+    CFB_TRY(launch_packed_plan(reinterpret_cast<const long long*>(lengths), pk->count, pk->first, pk->step, T, pk->t2_max,
+                               pk->n_rows, pk->n_tiles, tb, st),
             "packed layout tables");
     ++launches;
   }
@@ -801,7 +813,8 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
   if (pk || (!v && !(c0_var != nullptr && atoi(c0_var) == 0))) {
     if (pk) {
       CFB_TRY(launch_conv0_im2col_packed(feats, feats_dtype == CFB_BF16, reinterpret_cast<const long long*>(lengths),
-                                         ws + pl.a0, B, h->F0, T, conv_out(T), h->F1, h->Fh, pk->n_rows, tb, st),
+                                         ws + pl.a0, pk->first, pk->step, h->F0, T, conv_out(T), h->F1, h->Fh, pk->n_rows, tb,
+                                         st),
               "subsample conv 0 (gather)");
     } else {
       CFB_TRY(launch_conv0_im2col(feats, feats_dtype == CFB_BF16, ws + pl.a0, B, h->F0, T, pl.T1, h->F1, pl.Th, h->Fh, st),
@@ -1055,8 +1068,11 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     const bool last = (l == L - 1);
     if (last && pk) {
       // the dense (B, T', d) result of the reference API: zeros, then the valid rows of every slot (packed.cu)
-      const size_t out_bytes = static_cast<size_t>(B) * pk->t2_max * d * (out_dtype == CFB_BF16 ? 2 : 4);
-      if (cudaMemsetAsync(encoded, 0, out_bytes, st) != cudaSuccess) return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: memset failed");
+      if (pk->prologue) {
+        const size_t out_bytes = static_cast<size_t>(B) * pk->t2_max * d * (out_dtype == CFB_BF16 ? 2 : 4);
+        if (cudaMemsetAsync(encoded, 0, out_bytes, st) != cudaSuccess)
+          return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: memset failed");
+      }
       CFB_TRY(launch_layernorm_scatter(x, h->at<float>(lw.ln_g[4]), h->at<float>(lw.ln_b[4]), encoded, out_dtype == CFB_BF16,
                                        N, d, tb.row_out, st),
               "norm_out");
@@ -1109,6 +1125,7 @@ int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t
     return fail(h, CFB_ERR_WORKSPACE, "cfb_forward: workspace too small or not 256-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int launches = 0;
+  set_pdl_auto(static_cast<long long>(B) * conv_out(conv_out(T)) <= 4096);
   // Utterances are independent, so a batch can run as two half-batches on two streams (fork / join with events,
   // capturable): the halves' kernels interleave on the GPU -- one half's memory-bound LayerNorms and kernel tails
   // overlap the other half's GEMMs instead of leaving the tensor cores idle.  Results are identical to the
@@ -1137,10 +1154,36 @@ int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t
   return rc != CFB_OK ? rc : rc1;
 }
 
+}  // extern "C"
+
+// A packed batch of >= 2 utterances runs as two interleaved groups (even / odd utterances: balanced when the caller
+// sorts by length, as sharding.plan_shards does) on two streams, like cfb_forward's half-batches: the groups' kernels
+// interleave on the GPU, which matters most for SMALL shares (a rank of an 8-GPU job), where every kernel is a fraction
+// of a wave and latency-bound.  CFB_MICROBATCH=0 keeps one group.
+// Measured (r5b, cfg3 shares, ms per step with / without the split): 25 480 rows 13.31 / 13.25, 6 500 rows 4.34 / 4.22,
+// 3 100 rows 2.93 / 3.07 -- it pays once a launch no longer fills the machine.
+constexpr int kSmallBatchRows = 4096;
+static bool packed_split(const cfb_handle* h, int B, int n_rows) {
+  static const char* force = getenv("CFB_PACKED_SPLIT");  // 0 / 1 forces
+  if (force != nullptr) return atoi(force) != 0 && B >= 2 && !h->profiling;
+  return micro_batching_enabled() && B >= 2 && !h->profiling && n_rows <= kSmallBatchRows;
+}
+static size_t packed_plan_bytes(const cfb_handle* h, int B, int T, const PackedShape& ps) {
+  return make_plan(h, B, T, ps.n_rows, ps.t2_max, ps.count, ps.n_tiles).total;
+}
+static size_t packed_workspace_need(const cfb_handle* h, const int64_t* lengths_host, int B, int T) {
+  size_t need = packed_plan_bytes(h, B, T, packed_shape(lengths_host, B, T));
+  if (B >= 2)
+    need = std::max(need, packed_plan_bytes(h, B, T, packed_shape(lengths_host, B, T, 0, 2)) +
+                              packed_plan_bytes(h, B, T, packed_shape(lengths_host, B, T, 1, 2)));
+  return need;
+}
+
+extern "C" {
+
 int cfb_packed_workspace_bytes(const cfb_handle* h, const int64_t* lengths_host, int B, int T, size_t* out) {
   if (!h || !out || B < 1 || T < 1) return fail(h, CFB_ERR_INVALID_ARG, "cfb_packed_workspace_bytes: bad argument");
-  const PackedShape ps = packed_shape(lengths_host, B, T);
-  *out = make_plan(h, B, T, ps.n_rows, ps.t2_max, B, ps.n_tiles).total;
+  *out = packed_workspace_need(h, lengths_host, B, T);
   return CFB_OK;
 }
 
@@ -1160,14 +1203,38 @@ int cfb_forward_packed(cfb_handle* h, const void* feats, int feats_dtype, const 
   if (h->validate) return fail(h, CFB_ERR_UNSUPPORTED, "cfb_forward_packed: the fp32 validation path runs dense batches only");
   if (h->has_out_proj) return fail(h, CFB_ERR_UNSUPPORTED, "cfb_forward_packed: out_proj (feat_out != d_model) runs dense batches only");
   if (B > 2048) return fail(h, CFB_ERR_UNSUPPORTED, "cfb_forward_packed: at most 2048 utterances per call");
-  const PackedShape ps = packed_shape(lengths_host, B, T);
-  if (ws_bytes < make_plan(h, B, T, ps.n_rows, ps.t2_max, B, ps.n_tiles).total || (reinterpret_cast<uintptr_t>(workspace) & 255))
+  if (ws_bytes < packed_workspace_need(h, lengths_host, B, T) || (reinterpret_cast<uintptr_t>(workspace) & 255))
     return fail(h, CFB_ERR_WORKSPACE, "cfb_forward_packed: workspace too small or not 256-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int launches = 0;
-  int rc = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, workspace,
-                         reinterpret_cast<cudaStream_t>(stream), &launches, B, &ps);
+  const PackedShape ps = packed_shape(lengths_host, B, T);
+  set_pdl_auto(ps.n_rows <= kSmallBatchRows);
+  if (!packed_split(h, B, ps.n_rows)) {
+    int rc = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, workspace, st, &launches, B, &ps);
+    h->launches = launches;
+    return rc;
+  }
+  PackedShape g0 = packed_shape(lengths_host, B, T, 0, 2), g1 = packed_shape(lengths_host, B, T, 1, 2);
+  g1.prologue = false;  // group 0's range computes encoded_len and clears the result before the fork
+  // encoded_len / the cleared result are needed by both groups: enqueue them, then fork
+  if (launch_lengths(reinterpret_cast<const long long*>(lengths), encoded_len, B, T, 2, st) != 0)
+    return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: lengths kernel failed");
+  ++launches;
+  g0.prologue = false;
+  {
+    const size_t out_bytes = static_cast<size_t>(B) * g0.t2_max * h->d * (out_dtype == CFB_BF16 ? 2 : 4);
+    if (cudaMemsetAsync(encoded, 0, out_bytes, st) != cudaSuccess) return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: memset failed");
+  }
+  uint8_t* ws1 = reinterpret_cast<uint8_t*>(workspace) + packed_plan_bytes(h, B, T, g0);
+  if (cudaEventRecord(h->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0) != cudaSuccess)
+    return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: stream fork failed");
+  int rc = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, workspace, st, &launches, B, &g0);
+  int rc1 = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, ws1, h->aux_stream, &launches,
+                          B, &g1);
+  cudaEventRecord(h->ev_join, h->aux_stream);
+  cudaStreamWaitEvent(st, h->ev_join, 0);
   h->launches = launches;
-  return rc;
+  return rc != CFB_OK ? rc : rc1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -21,9 +21,12 @@ __device__ __forceinline__ int clip_len(const long long* lengths, int b, int T) 
   return v < 0 ? 0 : (v > T ? T : static_cast<int>(v));
 }
 
-// One CTA.  Thread b owns utterance b for the prefix sums; all threads then fill the per-row tables.
-__global__ void __launch_bounds__(kPlanThreads) packed_plan_kernel(const long long* __restrict__ lengths, int B, int T,
-                                                                   int T2, int n_rows, int n_tiles, PackedTables tb) {
+// One CTA.  The launch lays out the GROUP of utterances first, first + step, ... (B of them; the engine runs a batch as
+// two interleaved groups on two streams).  Slot k of the group holds utterance first + k * step; tiles / row_out carry
+// the utterance's index in the whole batch.
+__global__ void __launch_bounds__(kPlanThreads) packed_plan_kernel(const long long* __restrict__ lengths, int B, int first,
+                                                                   int step, int T, int T2, int n_rows, int n_tiles,
+                                                                   PackedTables tb) {
   extern __shared__ int sh[];  // [B] slot rows -> exclusive prefix (row0), [B] query tiles -> exclusive prefix, [B] t2
   int* s_row0 = sh;
   int* s_tile0 = sh + B;
@@ -32,7 +35,7 @@ __global__ void __launch_bounds__(kPlanThreads) packed_plan_kernel(const long lo
   pdl_launch_dependents();
   pdl_wait();
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const int len = clip_len(lengths, b, T);
+    const int len = clip_len(lengths, first + b * step, T);
     const int t1 = (len + 1) >> 1;
     const int t2 = (t1 + 1) >> 1;
     const int rows = (t2 + kPackGap + kPackAlign - 1) / kPackAlign * kPackAlign;
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(kPlanThreads) packed_plan_kernel(const long lo
     tb.seq_rows[b] = s_rows[b];
     const int nq = (s_rows[b] + 127) / 128;
     for (int q = 0; q < nq; ++q)
-      if (s_tile0[b] + q < n_tiles) tb.tiles[s_tile0[b] + q] = make_int4(b, q * 128, s_row0[b], s_rows[b]);
+      if (s_tile0[b] + q < n_tiles) tb.tiles[s_tile0[b] + q] = make_int4(first + b * step, q * 128, s_row0[b], s_rows[b]);
   }
   for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
     int lo = 0, hi = B - 1;  // last b with row0[b] <= r
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(kPlanThreads) packed_plan_kernel(const long lo
     const int t = r - s_row0[lo];
     const bool valid = t < s_t2[lo];
     tb.row_t[r] = valid ? t : -1;
-    tb.row_out[r] = valid ? lo * T2 + t : -1;
+    tb.row_out[r] = valid ? (first + lo * step) * T2 + t : -1;
     if ((r & (kPackAlign - 1)) == 0) tb.blk_seq[r / kPackAlign] = lo;
   }
 }
@@ -81,15 +84,16 @@ constexpr int kA0Cols = kConv0Cols;
 template <typename TIn>
 __global__ void __launch_bounds__(256) conv0_im2col_packed_kernel(const TIn* __restrict__ feats,
                                                                   const long long* __restrict__ lengths,
-                                                                  bf16* __restrict__ a0, int F, int T, int T1, int F1,
-                                                                  int Fh, int n_rows, PackedTables tb) {
+                                                                  bf16* __restrict__ a0, int first, int step, int F, int T,
+                                                                  int T1, int F1, int Fh, int n_rows, PackedTables tb) {
   extern __shared__ float patch[];  // [F + 2][2*kS1T + 2]
   const int pw = 2 * kS1T + 2;
   pdl_launch_dependents();
   pdl_wait();
   const int blk = blockIdx.x;
-  const int b = tb.blk_seq[blk];
-  const int t1_0 = 2 * (blk * kPackAlign - tb.seq_row0[b]);  // first local first-conv row of this block
+  const int k = tb.blk_seq[blk];  // slot of the group
+  const int b = first + k * step;  // utterance of the batch
+  const int t1_0 = 2 * (blk * kPackAlign - tb.seq_row0[k]);  // first local first-conv row of this block
   const int len = clip_len(lengths, b, T);
   const int t1_live = min((len + 1) >> 1, T1 - 1);  // local rows 0 .. t1_live are computed, the rest are zero rows
   const TIn* xb = feats + static_cast<long long>(b) * F * T;
@@ -213,26 +217,26 @@ __global__ void __launch_bounds__(256) layernorm_scatter_kernel(const float* __r
 
 }  // namespace
 
-int launch_packed_plan(const long long* lengths, int B, int T, int T2, int n_rows, int n_tiles, const PackedTables& tb,
-                       cudaStream_t st) {
+int launch_packed_plan(const long long* lengths, int B, int first, int step, int T, int T2, int n_rows, int n_tiles,
+                       const PackedTables& tb, cudaStream_t st) {
   if (B <= 0) return 0;
   const size_t smem = static_cast<size_t>(4) * B * sizeof(int);
   if (smem > 48 * 1024) return -1;
-  launch_pdl(packed_plan_kernel, dim3(1), dim3(kPlanThreads), smem, st, lengths, B, T, T2, n_rows, n_tiles, tb);
+  launch_pdl(packed_plan_kernel, dim3(1), dim3(kPlanThreads), smem, st, lengths, B, first, step, T, T2, n_rows, n_tiles, tb);
   return static_cast<int>(cudaGetLastError());
 }
 
-int launch_conv0_im2col_packed(const void* feats, bool feats_bf16, const long long* lengths, void* a0, int B, int F, int T,
-                               int T1, int F1, int Fh, int n_rows, const PackedTables& tb, cudaStream_t st) {
-  if (B <= 0 || n_rows <= 0) return 0;
+int launch_conv0_im2col_packed(const void* feats, bool feats_bf16, const long long* lengths, void* a0, int first, int step,
+                               int F, int T, int T1, int F1, int Fh, int n_rows, const PackedTables& tb, cudaStream_t st) {
+  if (n_rows <= 0) return 0;
   const size_t smem = static_cast<size_t>(F + 2) * (2 * kS1T + 2) * sizeof(float);
   const dim3 grid(n_rows / kPackAlign);
   if (feats_bf16)
     launch_pdl(conv0_im2col_packed_kernel<bf16>, grid, dim3(256), smem, st, reinterpret_cast<const bf16*>(feats), lengths,
-               reinterpret_cast<bf16*>(a0), F, T, T1, F1, Fh, n_rows, tb);
+               reinterpret_cast<bf16*>(a0), first, step, F, T, T1, F1, Fh, n_rows, tb);
   else
     launch_pdl(conv0_im2col_packed_kernel<float>, grid, dim3(256), smem, st, reinterpret_cast<const float*>(feats), lengths,
-               reinterpret_cast<bf16*>(a0), F, T, T1, F1, Fh, n_rows, tb);
+               reinterpret_cast<bf16*>(a0), first, step, F, T, T1, F1, Fh, n_rows, tb);
   return static_cast<int>(cudaGetLastError());
 }
 

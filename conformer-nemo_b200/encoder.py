@@ -314,6 +314,10 @@ class ConformerEncoder(nn.Module):
             handle = ctypes.c_void_p()
             _lib.check(lib.cfb_create(ctypes.byref(cfg), index, ctypes.byref(handle)), None, "cfb_create")
             self._handle, self._handle_device = handle, index
+        # cfb_set_weight copies with a blocking cudaMemcpy on the legacy default stream, which does not order itself after
+        # torch's non-blocking side streams: make sure whatever produced the parameters (a .to() enqueued on the current
+        # stream, the dtype conversions below) has completed before the library reads them
+        torch.cuda.current_stream(device).synchronize()
         sd = self.state_dict()
         # sinusoid frequencies computed with the same torch expression as the reference (multi_head_attention.py:238-241)
         sd["pos_enc.div_term"] = torch.exp(
@@ -325,6 +329,8 @@ class ConformerEncoder(nn.Module):
             if t.dtype not in _DTYPES:
                 t = t.float()
             t = t.contiguous()
+            if t.is_cuda:
+                torch.cuda.current_stream(t.device).synchronize()  # a conversion just enqueued must have finished
             shape = (ctypes.c_int64 * max(t.dim(), 1))(*t.shape)
             _lib.check(lib.cfb_set_weight(self._handle, key.encode(), ctypes.c_void_p(t.data_ptr()), _DTYPES[t.dtype],
                                           shape, t.dim()), self._handle, f"cfb_set_weight({key})")

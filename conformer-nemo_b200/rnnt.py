@@ -162,6 +162,19 @@ class GreedyBatchedRNNTInfer:
         """Call after changing decoder / joint parameters (they are re-read on the next call)."""
         self._packed = None
 
+    def _sources(self):
+        dec, jn = self.decoder, self.joint
+        lstm = dec.prediction["dec_rnn"].lstm
+        out = [m for m in jn.joint_net if isinstance(m, nn.Linear)][-1]
+        return (dec.prediction["embed"].weight, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0,
+                jn.pred.weight, jn.pred.bias, jn.enc.weight, jn.enc.bias, out.weight, out.bias)
+
+    def _fingerprint(self):
+        """Identity of the source parameters: storage, dtype and in-place version counter.  The kernel decodes from fp32
+        COPIES of them, so ``decoder.half()``, ``.to(dtype)``, re-assigning a Parameter or an in-place update (optimizer
+        step, ``load_state_dict``) must refresh the copies -- checked on every call (eleven tuple compares)."""
+        return tuple((p.data_ptr(), p.dtype, p._version) for p in self._sources())
+
     def _prepare(self, device):
         f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
         dec, jn = self.decoder, self.joint
@@ -177,7 +190,7 @@ class GreedyBatchedRNNTInfer:
         w.num_classes_with_blank, w.activation = jn.num_classes_with_blank, _ACTIVATIONS[jn.activation]
         for k, v in t.items():
             setattr(w, k, ctypes.cast(ctypes.c_void_p(v.data_ptr()), ctypes.POINTER(ctypes.c_float)))
-        self._packed = (w, t, device)
+        self._packed = (w, t, device, self._fingerprint())
 
     @torch.no_grad()
     def decode_arrays(self, encoder_output: torch.Tensor, encoded_lengths: torch.Tensor, max_tokens: Optional[int] = None):
@@ -189,7 +202,7 @@ class GreedyBatchedRNNTInfer:
         if not encoder_output.is_cuda:
             raise RuntimeError("GreedyBatchedRNNTInfer (B200) has no CPU path: encoder_output must be a CUDA tensor")
         device = encoder_output.device
-        if self._packed is None or self._packed[2] != device:
+        if self._packed is None or self._packed[2] != device or self._packed[3] != self._fingerprint():
             self._prepare(device)
         w = self._packed[0]
         b, d, t = encoder_output.shape

@@ -273,3 +273,49 @@ def load_reference_sample_greedy_class():
     """The reference's sample-level ``GreedyRNNTInfer`` (rnnt_greedy_decoding.py:191), from the same unmodified module."""
     load_reference_rnnt_classes()
     return sys.modules["nemo.collections.asr.parts.submodules.rnnt_greedy_decoding"].GreedyRNNTInfer
+
+
+def load_reference_wer_class():
+    """Returns the reference ``WER`` metric class (metrics/wer.py:67), executed unmodified; its greedy CTC collapse is
+    ``WER.ctc_decoder_predictions_tensor`` (:122-188).  wer.py imports ``editdistance`` and ``torchmetrics`` (both absent
+    here): ``editdistance`` gets an inert stand-in (the collapse never calls it) and ``torchmetrics.Metric`` a minimal base
+    class that accepts the constructor keywords and ``add_state`` calls WER makes."""
+    load_reference_rnnt_classes()  # stub packages, nemo.utils.logging, rnnt_utils.Hypothesis
+    name = "nemo.collections.asr.metrics.wer"
+    if name in sys.modules:
+        return sys.modules[name].WER
+    if "editdistance" not in sys.modules:
+        ed = types.ModuleType("editdistance")
+        ed.eval = lambda a, b: (_ for _ in ()).throw(NotImplementedError("editdistance stand-in"))
+        sys.modules["editdistance"] = ed
+    if "torchmetrics" not in sys.modules:
+        tm = types.ModuleType("torchmetrics")
+
+        class Metric:
+            def __init__(self, *args, **kwargs):
+                pass
+
+            def add_state(self, name, default, dist_reduce_fx=None, persistent=False):
+                setattr(self, name, default)
+
+        tm.Metric = Metric
+        sys.modules["torchmetrics"] = tm
+    _stub_package("nemo.collections.asr.metrics", os.path.join(REFERENCE_ROOT, "nemo/collections/asr/metrics"))
+    utils = sys.modules["nemo.utils"]
+    if not hasattr(utils.logging, "info"):
+        import logging as _logging
+
+        utils.logging = _logging.getLogger("nemo_stub")
+    return importlib.import_module(name).WER
+
+
+def reference_ctc_collapse(predictions, lengths, blank_id: int, fold_consecutive: bool = True):
+    """Token ids per utterance as the reference's ``WER.ctc_decoder_predictions_tensor`` produces them.  The method returns
+    text, so the vocabulary handed to WER is one distinct private-use character per class: text <-> ids is a bijection."""
+    import torch
+
+    wer = load_reference_wer_class()(vocabulary=[chr(0xE000 + i) for i in range(blank_id)], fold_consecutive=fold_consecutive,
+                                     log_prediction=False)
+    lens = None if lengths is None else torch.as_tensor(lengths)
+    texts = wer.ctc_decoder_predictions_tensor(torch.as_tensor(predictions), lens)
+    return [[ord(c) - 0xE000 for c in t] for t in texts]

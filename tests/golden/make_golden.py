@@ -33,6 +33,8 @@ CASES = {
     "featout_d64": (dict(feat_in=80, n_layers=1, d_model=64, n_heads=4, feat_out=48), 4, 2, 64, [64, 33], False),
     "nolen_d64": (dict(feat_in=80, n_layers=1, d_model=64, n_heads=4), 5, 1, 45, None, False),
     "noxscale_d64": (dict(feat_in=80, n_layers=1, d_model=64, n_heads=4, xscaling=False), 6, 2, 50, [50, 1], False),
+    # full depth of the Large recipes (conformer_transducer_bpe.yaml:110), small B / T: pins the oracle's drift over 17 layers
+    "large17_d512": (dict(feat_in=80, n_layers=17, d_model=512, n_heads=8), 7, 2, 300, [300, 173], False),
 }
 
 
@@ -42,7 +44,10 @@ def checksums(sd):
 
 def main():
     torch.set_num_threads(1)  # fixed reduction order
+    only = set(sys.argv[1:])
     for name, (kw, seed, b, t, lengths, store) in CASES.items():
+        if only and name not in only:
+            continue
         cfg = EncoderConfig(**kw)
         sd = random_state_dict(cfg, seed)
         enc = build_reference_encoder(cfg, sd)
@@ -67,6 +72,8 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
         print(name, tuple(y.shape), ylen.tolist())
 
+    if only:
+        return
     # calc_length pins (reference function, float32 arithmetic inside)
     from nemo.collections.asr.parts.submodules.subsampling import calc_length
 

@@ -139,6 +139,9 @@ def test_service_covers_every_utterance_once_and_bounds_padding():
         assert svc.padding_fraction() < 0.2  # 100-frame buckets on 10-1200 frame utterances
         for b in svc:
             assert b.audio_signal.shape == (len(b.indices), max(lengths[i] for i in b.indices))
+            # the staged batch is a CONTIGUOUS view of its slot: the H2D copy is then one async copy from pinned memory
+            assert b.audio_signal.is_contiguous()
+            assert b.audio_signal.data_ptr() == svc._audio[b.slot].data_ptr()
             assert b.audio_lengths.tolist() == [lengths[i] for i in b.indices]
             assert b.sample_ids.tolist() == b.indices
             for row, i in enumerate(b.indices):
@@ -154,6 +157,15 @@ def test_service_pinned_staging_on_gpu():
     lengths, load, svc = _service(2, 1, device="cuda", n=30)
     assert all(buf.is_pinned() for buf in svc._audio)
     total = 0
+    staged = []
+    orig = svc._collate
+
+    def spy(idx, slot):  # what goes into .to(device): must be a contiguous view of pinned memory (asynchronous copy)
+        out = orig(idx, slot)
+        staged.append((out[0].is_contiguous(), out[0].is_pinned()))
+        return out
+
+    svc._collate = spy
     for b in svc:
         svc.wait(b)
         assert b.audio_signal.is_cuda and b.audio_lengths.is_cuda
@@ -163,6 +175,7 @@ def test_service_pinned_staging_on_gpu():
         assert b.audio_lengths.cpu().tolist() == [lengths[i] for i in b.indices]
         total += len(b.indices)
     assert total == len(svc.plan.rank_indices(1)) > 0
+    assert staged and all(c and p for c, p in staged), staged
 
 
 def _gloo_collation_worker(rank, world, port, q):

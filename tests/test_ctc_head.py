@@ -49,6 +49,56 @@ def test_oracle_matches_live_reference_when_mounted():
     assert float((ho.ctc_head_forward(sd, x) - want).abs().max()) == 0.0
 
 
+def _collapse_golden():
+    z = np.load(os.path.join(GOLDEN, "ctc_collapse.npz"))
+    for n in range(int(z["n_cases"])):
+        k = f"c{n}"
+        lens = z[k + "_lens"]
+        want = [z[k + "_tokens"][i, :c].tolist() for i, c in enumerate(z[k + "_count"])]
+        yield torch.from_numpy(z[k + "_pred"]), (torch.from_numpy(lens) if lens.size else None), int(z[k + "_blank"]), \
+            bool(z[k + "_fold"]), want
+
+
+def test_greedy_collapse_matches_reference_golden():
+    """The collapse pinned to the UNMODIFIED reference (WER.ctc_decoder_predictions_tensor, metrics/wer.py:122-188; vectors
+    from tests/golden/make_golden_ctc_collapse.py): the oracle restatement and the product's host path."""
+    n = 0
+    for pred, lens, blank, fold, want in _collapse_golden():
+        if not fold:
+            # fold_consecutive=False (wer.py:165-169) keeps every non-blank frame: no recipe selects it and the product
+            # API has no such switch; the vectors are there to show the generator exercises the reference's other branch
+            assert want == [[p for p in (row[: int(lens[i])] if lens is not None else row) if p != blank]
+                            for i, row in enumerate(pred.tolist())]
+            continue
+        assert ho.greedy_collapse(pred, None if lens is None else lens.tolist(), blank) == want
+        assert cn.ctc_greedy_decode(pred, lens, blank) == want
+        n += 1
+    assert n >= 10
+
+
+def test_greedy_collapse_matches_live_reference_when_mounted():
+    from oracle import reference_loader as rl
+
+    if not rl.reference_available():
+        pytest.skip("reference tree not mounted")
+    g = torch.Generator().manual_seed(5)
+    for v in (3, 29, 129):
+        pred = torch.randint(0, v + 1, (7, 61), generator=g)
+        pred[torch.rand(7, 61, generator=g) < 0.5] = v
+        lens = torch.randint(0, 62, (7,), generator=g)
+        want = rl.reference_ctc_collapse(pred, lens, v)
+        assert ho.greedy_collapse(pred, lens.tolist(), v) == want
+        assert cn.ctc_greedy_decode(pred, lens, v) == want
+        assert cn.ctc_greedy_decode(pred, None, v) == rl.reference_ctc_collapse(pred, None, v)
+
+
+@pytest.mark.gpu
+def test_gpu_collapse_kernel_matches_reference_golden():
+    for pred, lens, blank, fold, want in _collapse_golden():
+        if fold:
+            assert cn.ctc_greedy_decode(pred.cuda(), None if lens is None else lens.cuda(), blank) == want
+
+
 def test_greedy_collapse_cases():
     blank = 4
     pred = torch.tensor([[1, 1, 4, 1, 2, 2, 4, 4, 3, 3], [4, 4, 4, 4, 4, 4, 4, 4, 4, 4], [0, 0, 0, 1, 4, 0, 2, 2, 2, 2]])

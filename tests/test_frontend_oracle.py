@@ -30,7 +30,7 @@ def test_oracle_matches_reference_golden(name):
     assert float((y - z["features"]).abs().max()) <= 1e-5
 
 
-def test_mel_filters_are_slaney_unit_area_triangles():
+def test_mel_filters_restated_from_librosa_unpinned_are_slaney_unit_area_triangles():
     fb = fo.slaney_mel_filters(16000, 512, 80, 0.0, None)
     assert fb.shape == (80, 257) and fb.dtype == np.float32 and (fb >= 0).all()
     z = load(CASES[0])

@@ -50,11 +50,11 @@ def main():
         for b, (h, r) in enumerate(zip(hyps, want)):
             utts += 1
             symbols += len(r.tokens)
-            if h.y_sequence.tolist() != r.tokens or list(h.timestep) != r.timesteps:
-                first = next((i for i, (a, c) in enumerate(zip(h.y_sequence.tolist(), r.tokens)) if a != c), min(len(h.y_sequence), len(r.tokens)))
-                # a difference is a near-tie if the oracle's own top-1 / top-2 gap at the first differing symbol is at the level of
-                # fp32 summation-order noise (the reference itself differs between its CPU and CUDA runs there)
-                margin = r.margins[first] if first < len(r.margins) else float("nan")
+            div = ro.first_divergence(h.y_sequence.tolist(), list(h.timestep), r)
+            if div is not None:
+                # a difference is a near-tie if the oracle's own top-1 / top-2 gap AT THE DECISION THAT DIFFERS (blank or symbol)
+                # is at the level of fp32 summation-order noise (the reference itself differs between its CPU and CUDA runs there)
+                first, margin = div
                 bad.append(dict(case=case, utt=b, dims=(e, p, j, v), B=B, T=T, max_symbols=ms, act=act, cluster=use_cluster,
                                 first_difference=first, got=len(h.y_sequence), want=len(r.tokens), oracle_margin_there=margin,
                                 near_tie=bool(margin < 2e-6)))
