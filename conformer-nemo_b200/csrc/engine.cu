@@ -67,6 +67,10 @@ struct cfb_handle {
   // two-stream micro-batching (see cfb_forward): the second half of a batch runs on an auxiliary stream
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // packed batches may run as up to kMaxGroups interleaved groups: group 0 on the caller's stream, g on group_stream[g]
+  static constexpr int kMaxGroups = 4;
+  cudaStream_t group_stream[kMaxGroups] = {};
+  cudaEvent_t group_join[kMaxGroups] = {};
   mutable std::string err;
   // optional per-launch event timing
   bool profiling = false;
@@ -309,6 +313,15 @@ int cfb_create(const cfb_config* cfg, int device, cfb_handle** out) {
     delete h;
     return bad(CFB_ERR_CUDA, "could not create the auxiliary stream / events");
   }
+  h->group_stream[1] = h->aux_stream;
+  h->group_join[1] = h->ev_join;
+  for (int g = 2; g < cfb_handle::kMaxGroups; ++g) {
+    if (cudaStreamCreateWithFlags(&h->group_stream[g], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->group_join[g], cudaEventDisableTiming) != cudaSuccess) {
+      delete h;
+      return bad(CFB_ERR_CUDA, "could not create the group streams / events");
+    }
+  }
   *out = h;
   return CFB_OK;
 }
@@ -318,6 +331,10 @@ void cfb_destroy(cfb_handle* h) {
   cudaSetDevice(h->device);
   if (h->arena) cudaFree(h->arena);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  for (int g = 2; g < cfb_handle::kMaxGroups; ++g) {
+    if (h->group_stream[g]) cudaStreamDestroy(h->group_stream[g]);
+    if (h->group_join[g]) cudaEventDestroy(h->group_join[g]);
+  }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (auto& e : h->ev_pool) cudaEventDestroy(e);
@@ -1156,26 +1173,34 @@ int cfb_forward(cfb_handle* h, const void* feats, int feats_dtype, const int64_t
 
 }  // extern "C"
 
-// A packed batch of >= 2 utterances runs as two interleaved groups (even / odd utterances: balanced when the caller
-// sorts by length, as sharding.plan_shards does) on two streams, like cfb_forward's half-batches: the groups' kernels
+// A small packed batch runs as interleaved groups (utterances g, g + G, ...: balanced when the caller sorts by length,
+// as sharding.plan_shards does) on their own streams, like cfb_forward's half-batches: the groups' kernels
 // interleave on the GPU, which matters most for SMALL shares (a rank of an 8-GPU job), where every kernel is a fraction
 // of a wave and latency-bound.  CFB_MICROBATCH=0 keeps one group.
-// Measured (r5b, cfg3 shares, ms per step with / without the split): 25 480 rows 13.31 / 13.25, 6 500 rows 4.34 / 4.22,
-// 3 100 rows 2.93 / 3.07 -- it pays once a launch no longer fills the machine.
+// Measured (r5b / r5e, cfg3 shares, ms per step): 25 480 rows 13.31 with two groups / 13.25 with one, 6 500 rows 4.41 /
+// 4.17, 3 100 rows (an 8-GPU share) 2.80 with one or two groups, 2.73 with three -- it only pays once a launch no
+// longer fills the machine.
 constexpr int kSmallBatchRows = 4096;
-static bool packed_split(const cfb_handle* h, int B, int n_rows) {
-  static const char* force = getenv("CFB_PACKED_SPLIT");  // 0 / 1 forces
-  if (force != nullptr) return atoi(force) != 0 && B >= 2 && !h->profiling;
-  return micro_batching_enabled() && B >= 2 && !h->profiling && n_rows <= kSmallBatchRows;
+// number of interleaved groups a packed batch runs as (1 = no split)
+static int packed_groups(const cfb_handle* h, int B, int n_rows) {
+  const char* force = getenv("CFB_PACKED_GROUPS");  // 1 .. 4 forces (read per call: tests switch it)
+  int g = 1;
+  if (force != nullptr) g = atoi(force);
+  else if (micro_batching_enabled() && n_rows <= kSmallBatchRows) g = 3;  // r5e: 1 / 2 / 3 / 4 groups 2.80 / 2.81 / 2.73 / 2.75 ms
+  if (h->profiling) g = 1;
+  g = std::min(std::min(g, B), cfb_handle::kMaxGroups);
+  return std::max(g, 1);
 }
 static size_t packed_plan_bytes(const cfb_handle* h, int B, int T, const PackedShape& ps) {
   return make_plan(h, B, T, ps.n_rows, ps.t2_max, ps.count, ps.n_tiles).total;
 }
 static size_t packed_workspace_need(const cfb_handle* h, const int64_t* lengths_host, int B, int T) {
-  size_t need = packed_plan_bytes(h, B, T, packed_shape(lengths_host, B, T));
-  if (B >= 2)
-    need = std::max(need, packed_plan_bytes(h, B, T, packed_shape(lengths_host, B, T, 0, 2)) +
-                              packed_plan_bytes(h, B, T, packed_shape(lengths_host, B, T, 1, 2)));
+  size_t need = 0;
+  for (int groups = 1; groups <= std::min(B, cfb_handle::kMaxGroups); ++groups) {
+    size_t sum = 0;
+    for (int g = 0; g < groups; ++g) sum += packed_plan_bytes(h, B, T, packed_shape(lengths_host, B, T, g, groups));
+    need = std::max(need, sum);
+  }
   return need;
 }
 
@@ -1209,32 +1234,41 @@ int cfb_forward_packed(cfb_handle* h, const void* feats, int feats_dtype, const 
   int launches = 0;
   const PackedShape ps = packed_shape(lengths_host, B, T);
   set_pdl_auto(ps.n_rows <= kSmallBatchRows);
-  if (!packed_split(h, B, ps.n_rows)) {
+  const int groups = packed_groups(h, B, ps.n_rows);
+  if (groups == 1) {
     int rc = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, workspace, st, &launches, B, &ps);
     h->launches = launches;
     return rc;
   }
-  PackedShape g0 = packed_shape(lengths_host, B, T, 0, 2), g1 = packed_shape(lengths_host, B, T, 1, 2);
-  g1.prologue = false;  // group 0's range computes encoded_len and clears the result before the fork
-  // encoded_len / the cleared result are needed by both groups: enqueue them, then fork
+  // encoded_len and the cleared result are needed by every group: enqueue them, then fork
   if (launch_lengths(reinterpret_cast<const long long*>(lengths), encoded_len, B, T, 2, st) != 0)
     return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: lengths kernel failed");
   ++launches;
-  g0.prologue = false;
   {
-    const size_t out_bytes = static_cast<size_t>(B) * g0.t2_max * h->d * (out_dtype == CFB_BF16 ? 2 : 4);
+    const size_t out_bytes = static_cast<size_t>(B) * ps.t2_max * h->d * (out_dtype == CFB_BF16 ? 2 : 4);
     if (cudaMemsetAsync(encoded, 0, out_bytes, st) != cudaSuccess) return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: memset failed");
   }
-  uint8_t* ws1 = reinterpret_cast<uint8_t*>(workspace) + packed_plan_bytes(h, B, T, g0);
-  if (cudaEventRecord(h->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0) != cudaSuccess)
-    return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: stream fork failed");
-  int rc = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, workspace, st, &launches, B, &g0);
-  int rc1 = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, ws1, h->aux_stream, &launches,
-                          B, &g1);
-  cudaEventRecord(h->ev_join, h->aux_stream);
-  cudaStreamWaitEvent(st, h->ev_join, 0);
+  if (cudaEventRecord(h->ev_fork, st) != cudaSuccess) return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: stream fork failed");
+  for (int g = 1; g < groups; ++g)
+    if (cudaStreamWaitEvent(h->group_stream[g], h->ev_fork, 0) != cudaSuccess)
+      return fail(h, CFB_ERR_CUDA, "cfb_forward_packed: stream fork failed");
+  int rc = CFB_OK;
+  uint8_t* wsg = reinterpret_cast<uint8_t*>(workspace);
+  for (int g = 0; g < groups; ++g) {
+    PackedShape gs = packed_shape(lengths_host, B, T, g, groups);
+    gs.prologue = false;
+    const int r = forward_range(h, feats, feats_dtype, lengths, B, T, encoded, out_dtype, encoded_len, wsg,
+                                g == 0 ? st : h->group_stream[g], &launches, B, &gs);
+    if (rc == CFB_OK) rc = r;
+    wsg += packed_plan_bytes(h, B, T, gs);
+  }
+  // always join, even after an error, so a capture in progress is not left with a dangling branch
+  for (int g = 1; g < groups; ++g) {
+    cudaEventRecord(h->group_join[g], h->group_stream[g]);
+    cudaStreamWaitEvent(st, h->group_join[g], 0);
+  }
   h->launches = launches;
-  return rc != CFB_OK ? rc : rc1;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -413,6 +413,13 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
   // 256-wide tiles halve the re-reads of A (the kernel is bound by L2->SM bandwidth, not by the tensor pipe)
   int bn = 128;
   if (g.N % 256 == 0) bn = 256;
+  {
+    // Small M (a rank's share of a sharded batch): 256-wide tiles of an N = 512 GEMM occupy a third of the machine and
+    // each runs the whole K loop; 128-wide tiles double the CTAs and shorten the critical path (the tiles are
+    // latency-bound there, not operand-bound).  CFB_GEMM_SMALL_BN=0 keeps 256.
+    static const bool small_bn = !(getenv("CFB_GEMM_SMALL_BN") != nullptr && atoi(getenv("CFB_GEMM_SMALL_BN")) == 0);
+    if (small_bn && bn == 256 && 2 * m_tiles * (g.N / 256) <= num_sms()) bn = 128;
+  }
   const int n_tiles = (g.N + bn - 1) / bn;
 
   CUtensorMap tmA, tmB;

@@ -111,6 +111,30 @@ def test_packed_graph_replay_and_persistent_attention_match_eager(monkeypatch):
     assert torch.equal(y0, y3)
 
 
+@pytest.mark.parametrize("groups", [1, 2, 3, 4])
+def test_packed_groups_on_their_own_streams_are_bit_identical(groups, monkeypatch):
+    """A small packed batch runs as interleaved groups of utterances on separate streams (engine.cu, packed_groups)."""
+    cfg = oc.EncoderConfig(feat_in=80, n_layers=2, d_model=256, n_heads=4)
+    enc = build(cfg, oc.random_state_dict(cfg, 4))
+    lens = [700, 650, 420, 333, 200, 64, 31]
+    x, length = oc.synthetic_batch(len(lens), 80, max(lens), lens, seed=9)
+    enc.packed = False
+    yd, yld = enc(audio_signal=x.cuda(), length=length.cuda())
+    yd = yd.clone()
+    monkeypatch.setenv("CFB_PACKED_GROUPS", str(groups))
+    enc.packed = True
+    n0 = None
+    for _ in range(2):
+        yp, ylp = enc(audio_signal=x.cuda(), length=length.cuda(), length_host=lens)
+        n0 = enc.last_launch_count()
+    assert torch.equal(yld, ylp)
+    for b in range(len(lens)):
+        n = int(yld[b])
+        assert torch.equal(yd[b, :, :n], yp[b, :, :n]), (groups, b)
+        assert float(yp[b, :, n:].abs().sum()) == 0.0
+    assert n0 > 0
+
+
 def test_auto_mode_packs_only_ragged_batches_with_host_lengths():
     cfg = oc.EncoderConfig(feat_in=80, n_layers=1, d_model=256, n_heads=4)
     enc = build(cfg, oc.random_state_dict(cfg, 1))

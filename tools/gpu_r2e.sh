@@ -1,0 +1,14 @@
+#!/bin/bash
+TAG=${1:-r5e}
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_packed.py -x -q -p no:cacheprovider 2>&1 | tail -3
+show() { python - "$1" <<'PY'
+import json,sys
+d=json.load(open(sys.argv[1]))
+print(sys.argv[1], {k:round(d[k],3) for k in ("value","ms_per_step","eager_ms_per_step")}, round(d["e2e"]["value"]), d["gpu_launches"]//d["steps"])
+PY
+}
+for g in 1 2 3 4; do for sh in 0/8 0/4; do
+  CFB_PACKED_GROUPS=$g timeout 300 python bench.py --workload cfg3 --share $sh --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_cfg3_g${g}_${sh/\//of}.json 2> gpurun_out/${TAG}_err.log || tail -3 gpurun_out/${TAG}_err.log
+  show gpurun_out/${TAG}_cfg3_g${g}_${sh/\//of}.json
+done; done

@@ -87,15 +87,15 @@ def main():
         enc.packed = False
         enc(audio_signal=x.cuda(), length=length.cuda())
         stage("encoder packed (one group)")
-        os.environ["CFB_PACKED_SPLIT"] = "0"
+        os.environ["CFB_PACKED_GROUPS"] = "1"
         enc.packed = True
         enc(audio_signal=x.cuda(), length=length.cuda(), length_host=lens)
         torch.cuda.synchronize()
         stage("encoder packed (two groups on two streams)")
-        os.environ["CFB_PACKED_SPLIT"] = "1"
+        os.environ["CFB_PACKED_GROUPS"] = "2"
         enc(audio_signal=x.cuda(), length=length.cuda(), length_host=lens)
         torch.cuda.synchronize()
-        os.environ.pop("CFB_PACKED_SPLIT", None)
+        os.environ.pop("CFB_PACKED_GROUPS", None)
     if want("ctc"):
         stage("ctc head + collapse")
         dec = cn.ConvASRDecoder(feat_in=256, num_classes=28).cuda()
