@@ -54,51 +54,6 @@ struct ConvDesc {
   int To = 0, Fo = 0;  // output extents
 };
 
-// row-complete GEMM with fused residual update and LayerNorm(s) (gemm_ln.cu):
-//   v = resid + alpha * (A W^T + bias);  y = LN1(v) if gamma1 else v;  out_f32 = y;  out_bf16 = LN2(y) if gamma2 else y
-// lens != null: rows at frames >= lens[row / frames_per_seq] are written as zeros in both outputs
-struct GemmLnDesc {
-  const void* A = nullptr;
-  long long lda = 0;
-  const void* W = nullptr;
-  long long ldw = 0;
-  int M = 0, N = 0, K = 0;
-  const float* bias = nullptr;
-  float alpha = 1.f;
-  const float* resid = nullptr;
-  long long ld_resid = 0;
-  const float* gamma1 = nullptr;
-  const float* beta1 = nullptr;
-  const float* gamma2 = nullptr;
-  const float* beta2 = nullptr;
-  float* out_f32 = nullptr;
-  long long ld_out_f32 = 0;
-  void* out_bf16 = nullptr;
-  long long ld_out_bf16 = 0;
-  const int32_t* lens = nullptr;
-  int frames_per_seq = 1;
-};
-int launch_gemm_ln(const GemmLnDesc& g, cudaStream_t st, std::string* err);
-
-// GEMM whose A operand is LayerNorm(x), produced by a prologue and kept resident in tensor memory (gemm_lnt.cu):
-//   [y = LN1(x) -> x_out (fp32)]  optional;  a = bf16(LN2(y or x));  D = a W^T with the EPI_SWISH / QKV / GLU / LINEAR
-//   epilogue (bf16 output).  K = d <= 512.
-struct GemmLnaDesc {
-  const float* x = nullptr;
-  long long ldx = 0;
-  int M = 0, N = 0, d = 0;
-  const float* gamma1 = nullptr;
-  const float* beta1 = nullptr;
-  float* x_out = nullptr;
-  const float* gamma2 = nullptr;
-  const float* beta2 = nullptr;
-  const void* W = nullptr;
-  long long ldw = 0;
-  int epi = EPI_LINEAR;
-  EpiParams ep;
-};
-int launch_gemm_lnt(const GemmLnaDesc& g, cudaStream_t st, std::string* err);
-
 struct AttnDesc {
   const void* qkv = nullptr;  // (B*T, 4*Dp)
   const void* pos = nullptr;  // (2T-1, ld_pos), this layer's columns start at pos

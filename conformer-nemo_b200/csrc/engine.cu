@@ -760,10 +760,6 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     return rc;
   };
 
-  // Row-complete GEMM with the residual update and the following LayerNorm(s) in its epilogue (gemm_ln.cu): the
-  // product path for d_model <= 512.  ln1 / ln2 index lw.ln_g / lw.ln_b of the given layers (-1 = none).
-  static const bool fused_env = getenv("CFB_FUSED_LN") != nullptr && atoi(getenv("CFB_FUSED_LN")) != 0;
-  const bool fused_ln = fused_env && !v && d <= 512 && !pk;
   // conv-module tail as one kernel (conv_tail.cu) whenever the shape allows it; CFB_FUSED_TAIL=0 keeps the two launches
   const char* tail_var = getenv("CFB_FUSED_TAIL");  // 0 = never, 2 = whenever the shape allows, unset = heuristic
   const bool tail_env = !(tail_var != nullptr && atoi(tail_var) == 0);
@@ -778,41 +774,7 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     const long long ctas = static_cast<long long>(pk ? 1 : B_total) * ((T2 + 127) / 128);
     const long long waves = (ctas + sms - 1) / sms;
     fused_tail = ctas * 100 >= waves * sms * 65;
-  }  // experimental: measured slower than GEMM + LayerNorm (gemm_ln.cu)
-  auto gemm_ln = [&](const void* A, long long lda, const Slot& W, long long ldw, int K, const Slot& bias, float alpha,
-                     bool resid, const LayerW* l1, int i1, const LayerW* l2, int i2, float* out_f32, void* out_bf16,
-                     long long ld_out, bool mask) -> int {
-    GemmLnDesc g;
-    g.A = A;
-    g.lda = lda;
-    g.W = h->arena + W.off;
-    g.ldw = ldw;
-    g.M = N;
-    g.N = d;
-    g.K = K;
-    g.bias = h->at<float>(bias);
-    g.alpha = alpha;
-    g.resid = resid ? reinterpret_cast<const float*>(ws + pl.x) : nullptr;
-    g.ld_resid = d;
-    if (l1) {
-      g.gamma1 = h->at<float>(l1->ln_g[i1]);
-      g.beta1 = h->at<float>(l1->ln_b[i1]);
-    }
-    if (l2) {
-      g.gamma2 = h->at<float>(l2->ln_g[i2]);
-      g.beta2 = h->at<float>(l2->ln_b[i2]);
-    }
-    g.out_f32 = out_f32;
-    g.ld_out_f32 = ld_out;
-    g.out_bf16 = out_bf16;
-    g.ld_out_bf16 = ld_out;
-    if (mask) {
-      g.lens = encoded_len;
-      g.frames_per_seq = T2;
-    }
-    ++launches;
-    return launch_gemm_ln(g, st, &err);
-  };
+  }
 
   // ---- lengths (subsampling.py:164-171)
   if (!pk || pk->prologue) {
@@ -878,11 +840,7 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     ++launches;
   }
   float* x = reinterpret_cast<float*>(ws + pl.x);
-  if (fused_ln) {
-    CFB_TRY(gemm_ln(ws + pl.y2, static_cast<long long>(F2) * C, h->sub_w3, static_cast<long long>(F2) * C, F2 * C,
-                    h->sub_b3, 1.f, false, nullptr, 0, &h->layers[0], 0, x, ws + pl.a, d, false),
-            "pre_encode.out");
-  } else {
+  {
     EpiParams ep;
     ep.bias = h->at<float>(h->sub_b3);
     ep.out = x;
@@ -904,84 +862,6 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
 
   const int32_t* lens = encoded_len;
   void* a = ws + pl.a;
-  if (fused_ln) {
-    for (int l = 0; l < L; ++l) {
-      const LayerW& lw = h->layers[l];
-      const bool last = (l == L - 1);
-      for (int f = 0; f < 2; ++f) {
-        if (f == 1) {
-          // -- self attention (conformer_modules.py:103-110); `a` holds norm_self_att(x)
-          EpiParams ep;
-          ep.bias = h->at<float>(lw.b_qkv);
-          ep.bias2 = h->at<float>(lw.b_qv);
-          ep.out = ws + pl.qkv;
-          ep.ldo = 4LL * Dp;
-          ep.qkv_dp = Dp;
-          CFB_TRY(gemm(a, d, lw.w_qkv, d, N, 3 * Dp, d, EPI_QKV, true, ep, "qkv projection"), "qkv projection");
-          AttnDesc ad;
-          ad.qkv = ws + pl.qkv;
-          ad.pos = ws + pl.pos + static_cast<size_t>(l) * Dp * h->esz();
-          ad.ld_pos = static_cast<long long>(L) * Dp;
-          ad.ctx = ws + pl.ctx;
-          ad.lens = lens;
-          ad.B = B;
-          ad.T = T2;
-          ad.H = H;
-          ad.dk = h->dk;
-          ad.dkp = h->dkp;
-          CFB_TRY(launch_attn_tc(ad, st, &err), "rel-pos attention");
-          ++launches;
-          // x += linear_out(ctx); a = norm_conv(x)
-          CFB_TRY(gemm_ln(ws + pl.ctx, Dp, lw.w_out, Dp, Dp, lw.b_out, 1.f, true, nullptr, 0, &lw, 2, x, a, d, false),
-                  "linear_out");
-          // -- convolution module (conformer_modules.py:112-114, 160-180)
-          EpiParams eg;
-          eg.bias = h->at<float>(lw.b_pw1);
-          eg.out = ws + pl.g;
-          eg.ldo = d;
-          eg.lens = lens;
-          eg.frames_per_seq = T2;
-          CFB_TRY(gemm(a, d, lw.w_pw1, d, N, 2 * d, d, EPI_GLU, true, eg, "pointwise_conv1+glu"), "pointwise_conv1+glu");
-          CFB_TRY(launch_depthwise(ws + pl.g, h->at<float>(lw.dw_taps), h->at<float>(lw.dw_bias), ws + pl.c, true, B, T2,
-                                   d, h->ksize, st),
-                  "depthwise conv");
-          ++launches;
-          // x += pointwise_conv2(c); a = norm_feed_forward2(x)
-          CFB_TRY(gemm_ln(ws + pl.c, d, lw.w_pw2, d, d, lw.b_pw2, 1.f, true, nullptr, 0, &lw, 3, x, a, d, false),
-                  "pointwise_conv2");
-        }
-        // -- feed forward (conformer_modules.py:98-101, 116-118); `a` holds the block's input LayerNorm
-        EpiParams e1;
-        e1.bias = h->at<float>(lw.ff_b1[f]);
-        e1.out = ws + pl.hbuf;
-        e1.ldo = dff;
-        CFB_TRY(gemm(a, d, lw.ff_w1[f], d, N, dff, d, EPI_SWISH, true, e1, "linear1+swish"), "linear1+swish");
-        if (f == 0) {
-          // x += 0.5 * linear2(h); a = norm_self_att(x)
-          CFB_TRY(gemm_ln(ws + pl.hbuf, dff, lw.ff_w2[0], dff, dff, lw.ff_b2[0], 0.5f, true, nullptr, 0, &lw, 1, x, a, d,
-                          false),
-                  "linear2");
-        } else if (!last) {
-          // x = norm_out(x + 0.5 * linear2(h)) (conformer_modules.py:120); a = next layer's norm_feed_forward1(x)
-          CFB_TRY(gemm_ln(ws + pl.hbuf, dff, lw.ff_w2[1], dff, dff, lw.ff_b2[1], 0.5f, true, &lw, 4, &h->layers[l + 1], 0,
-                          x, a, d, false),
-                  "linear2");
-        } else if (h->has_out_proj) {
-          CFB_TRY(gemm_ln(ws + pl.hbuf, dff, lw.ff_w2[1], dff, dff, lw.ff_b2[1], 0.5f, true, &lw, 4, nullptr, 0, nullptr,
-                          a, d, false),
-                  "linear2");
-        } else if (out_dtype == CFB_BF16) {
-          CFB_TRY(gemm_ln(ws + pl.hbuf, dff, lw.ff_w2[1], dff, dff, lw.ff_b2[1], 0.5f, true, &lw, 4, nullptr, 0, nullptr,
-                          encoded, d, true),
-                  "linear2");
-        } else {
-          CFB_TRY(gemm_ln(ws + pl.hbuf, dff, lw.ff_w2[1], dff, dff, lw.ff_b2[1], 0.5f, true, &lw, 4, nullptr, 0,
-                          reinterpret_cast<float*>(encoded), nullptr, d, true),
-                  "linear2");
-        }
-      }
-    }
-  } else {
   for (int l = 0; l < L; ++l) {
     const LayerW& lw = h->layers[l];
     // -- feed forward 1 (conformer_modules.py:98-101)
@@ -1110,7 +990,6 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
               "norm_out");
     }
     ++launches;
-  }
   }
   if (h->has_out_proj) {  // conformer_encoder.py:277-278
     EpiParams ep;
@@ -1307,75 +1186,6 @@ int cfb_op_gemm(int use_tc, int epilogue, const void* A, int64_t lda, const void
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = use_tc ? launch_gemm_tc(g, st, &err) : launch_gemm_simt(g, scratch, st, &err);
   return rc == 0 ? CFB_OK : op_fail(rc, err);
-}
-
-int cfb_op_gemm_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float alpha,
-                   const float* resid, int64_t ld_resid, const float* gamma1, const float* beta1, const float* gamma2,
-                   const float* beta2, int M, int N, int K, float* out_f32, int64_t ld_out_f32, void* out_bf16,
-                   int64_t ld_out_bf16, const int32_t* lens, int frames_per_seq, cfb_stream stream) {
-  GemmLnDesc g;
-  g.A = A;
-  g.lda = lda;
-  g.W = W;
-  g.ldw = ldw;
-  g.M = M;
-  g.N = N;
-  g.K = K;
-  g.bias = bias;
-  g.alpha = alpha;
-  g.resid = resid;
-  g.ld_resid = ld_resid;
-  g.gamma1 = gamma1;
-  g.beta1 = beta1;
-  g.gamma2 = gamma2;
-  g.beta2 = beta2;
-  g.out_f32 = out_f32;
-  g.ld_out_f32 = ld_out_f32;
-  g.out_bf16 = out_bf16;
-  g.ld_out_bf16 = ld_out_bf16;
-  g.lens = lens;
-  g.frames_per_seq = frames_per_seq > 0 ? frames_per_seq : 1;
-  std::string err;
-  int rc = launch_gemm_ln(g, reinterpret_cast<cudaStream_t>(stream), &err);
-  return rc == 0 ? CFB_OK : op_fail(rc, err);
-}
-
-static int op_gemm_lnt_impl(int epilogue, const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* x_out,
-                    const float* gamma2, const float* beta2, const void* W, int64_t ldw, const float* bias,
-                    const float* bias2, int M, int N, int d, void* out, int64_t ldo, const int32_t* lens,
-                    int frames_per_seq, int qkv_dp, cfb_stream stream) {
-  GemmLnaDesc g;
-  g.x = x;
-  g.ldx = ldx;
-  g.M = M;
-  g.N = N;
-  g.d = d;
-  g.gamma1 = gamma1;
-  g.beta1 = beta1;
-  g.x_out = x_out;
-  g.gamma2 = gamma2;
-  g.beta2 = beta2;
-  g.W = W;
-  g.ldw = ldw;
-  g.epi = epilogue;
-  g.ep.bias = bias;
-  g.ep.bias2 = bias2;
-  g.ep.out = out;
-  g.ep.ldo = ldo;
-  g.ep.lens = lens;
-  g.ep.frames_per_seq = frames_per_seq > 0 ? frames_per_seq : 1;
-  g.ep.qkv_dp = qkv_dp;
-  std::string err;
-  int rc = launch_gemm_lnt(g, reinterpret_cast<cudaStream_t>(stream), &err);
-  return rc == 0 ? CFB_OK : op_fail(rc, err);
-}
-
-int cfb_op_gemm_lnt(int epilogue, const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* x_out,
-                    const float* gamma2, const float* beta2, const void* W, int64_t ldw, const float* bias,
-                    const float* bias2, int M, int N, int d, void* out, int64_t ldo, const int32_t* lens,
-                    int frames_per_seq, int qkv_dp, cfb_stream stream) {
-  return op_gemm_lnt_impl(epilogue, x, ldx, gamma1, beta1, x_out, gamma2, beta2, W, ldw, bias, bias2, M, N, d, out, ldo,
-                          lens, frames_per_seq, qkv_dp, stream);
 }
 
 int cfb_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows, int d,

@@ -1019,11 +1019,14 @@ size_t rnnt_c4_fixed_bytes(int H, int J, int V1, int NQ, int B, int* umax, int* 
 bool g_c4_unusable = false;  // set when a cooperative cluster launch was refused once (the other kernel serves from then on)
 
 bool rnnt_c4_plan(int H, int J, int V1, int Bmax, int max_smem, RnntParams* p, int* grid, size_t* smem) {
-  // opt-in (CFB_RNNT_CLUSTER=1).  Measured (32 / 64 / 128 utterances x 500 frames): 11.3 / 17.2 / 29.5 ms against 12.1 / 19.1 /
-  // 32.8 ms for the row-partitioned kernel -- but Nsight Compute cannot replay a cooperative cluster launch (it aborts the
-  // process with LaunchFailed), so the kernel that can be profiled stays the default
+  // The default.  Measured (32 / 64 / 128 utterances x 500 frames): 11.3 / 17.2 / 29.5 ms against 12.1 / 19.1 / 32.8 ms for the
+  // row-partitioned kernel.  Nsight Compute cannot replay a cooperative cluster launch (it aborts the process with
+  // LaunchFailed), so the row-partitioned kernel is selected FOR PROFILING: when ncu has injected itself into the process
+  // (it exports NV_COMPUTE_PROFILER_PERFWORKS_DIR to its target, profiles/r5f_ncu_env_probe.log) or with CFB_RNNT_CLUSTER=0.
   const char* env = getenv("CFB_RNNT_CLUSTER");
-  if (env == nullptr || atoi(env) == 0 || g_c4_unusable || (H % 16) || (J % 16)) return false;
+  const bool profiler_attached = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr;
+  const bool want = env != nullptr ? atoi(env) != 0 : !profiler_attached;
+  if (!want || g_c4_unusable || (H % 16) || (J % 16)) return false;
   cudaFuncAttributes fa;
   if (cudaFuncGetAttributes(&fa, rnnt_greedy_c4_kernel) != cudaSuccess) return false;
   const size_t budget = static_cast<size_t>(max_smem) - fa.sharedSizeBytes;

@@ -160,27 +160,6 @@ CFB_API int cfb_op_gemm(int use_tensor_cores, int epilogue, const void* A, int64
                 float alpha, const int32_t* lens, int frames_per_seq, int qkv_dp, float* scratch,
                 cfb_stream stream);
 
-/* Row-complete GEMM with the residual update and the following LayerNorm(s) fused (tcgen05 path only, N <= 512):
- *   v = resid + alpha * (A W^T + bias)         (resid may be NULL)          conformer_modules.py:98-118
- *   y = LayerNorm(v; gamma1, beta1) if gamma1 else v                        (norm_out, :120)
- *   out_f32  (M x N fp32, may alias resid) = y
- *   out_bf16 (M x N bf16) = LayerNorm(y; gamma2, beta2) if gamma2 else y    (the next block's input normalisation)
- * lens != NULL: rows at frames >= lens[row / frames_per_seq] are written as zeros in both outputs. */
-CFB_API int cfb_op_gemm_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float alpha,
-                   const float* resid, int64_t ld_resid, const float* gamma1, const float* beta1, const float* gamma2,
-                   const float* beta2, int M, int N, int K, float* out_f32, int64_t ld_out_f32, void* out_bf16,
-                   int64_t ld_out_bf16, const int32_t* lens, int frames_per_seq, cfb_stream stream);
-
-/* GEMM with a LayerNorm prologue (tcgen05 path only, K = d <= 512 and a multiple of 64, bf16 output):
- *   y = LayerNorm(x; gamma1, beta1) -> x_out (fp32, may alias x)   if gamma1 != NULL (norm_out), else y = x
- *   out = epilogue( bf16(LayerNorm(y; gamma2, beta2)) W^T + bias )  epilogue in {LINEAR, SWISH, QKV, GLU}
- * The normalised rows live in TENSOR memory (the UMMA A operand is read from TMEM), so only the weight streams through
- * shared memory (gemm_lnt.cu).  Experimental: bit-identical to cfb_op_layernorm + cfb_op_gemm but slower. */
-CFB_API int cfb_op_gemm_lnt(int epilogue, const float* x, int64_t ldx, const float* gamma1, const float* beta1, float* x_out,
-                    const float* gamma2, const float* beta2, const void* W, int64_t ldw, const float* bias,
-                    const float* bias2, int M, int N, int d, void* out, int64_t ldo, const int32_t* lens,
-                    int frames_per_seq, int qkv_dp, cfb_stream stream);
-
 /* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5; conformer_modules.py:60-86). x fp32 (rows x d);
  * out_dtype CFB_BF16 / CFB_F32.  lens != NULL: rows at frames >= lens[seq] are written as zeros. */
 CFB_API int cfb_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows,

@@ -31,37 +31,6 @@ def op_gemm(use_tc, epi, A, W, bias=None, bias2=None, out=None, alpha=1.0, lens=
     return out
 
 
-def op_gemm_ln(A, W, bias, alpha=1.0, resid=None, ln1=None, ln2=None, out_f32=None, out_bf16=None, lens=None,
-               frames_per_seq=1):
-    """Fused residual + LayerNorm GEMM (cfb_op_gemm_ln).  ln1 / ln2: (gamma, beta) or None."""
-    lib = _lib.load_library()
-    M, K = A.shape
-    N = W.shape[0]
-    g1, b1 = ln1 if ln1 is not None else (None, None)
-    g2, b2 = ln2 if ln2 is not None else (None, None)
-    rc = lib.cfb_op_gemm_ln(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), float(alpha), ptr(resid),
-                            resid.stride(0) if resid is not None else 0, ptr(g1), ptr(b1), ptr(g2), ptr(b2), M, N, K,
-                            ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0, ptr(out_bf16),
-                            out_bf16.stride(0) if out_bf16 is not None else 0, ptr(lens), frames_per_seq, stream())
-    assert rc == 0, _lib.last_error(None)
-    torch.cuda.synchronize()
-
-
-def op_gemm_lna(epi, x, W, ln2, out, bias=None, bias2=None, ln1=None, x_out=None, lens=None, frames_per_seq=1, qkv_dp=0,
-                tmem=True):
-    """GEMM with LayerNorm prologue (cfb_op_gemm_lnt).  x (M,d) fp32; ln1 / ln2: (gamma, beta)."""
-    lib = _lib.load_library()
-    M, d = x.shape
-    N = W.shape[0]
-    g1, b1 = ln1 if ln1 is not None else (None, None)
-    fn = lib.cfb_op_gemm_lnt
-    rc = fn(epi, ptr(x), x.stride(0), ptr(g1), ptr(b1), ptr(x_out), ptr(ln2[0]), ptr(ln2[1]), ptr(W),
-                             W.stride(0), ptr(bias), ptr(bias2), M, N, d, ptr(out), out.stride(0), ptr(lens),
-                             frames_per_seq, qkv_dp, stream())
-    assert rc == 0, _lib.last_error(None)
-    torch.cuda.synchronize()
-
-
 def op_layernorm(x, gamma, beta, out, lens=None, frames_per_seq=1):
     lib = _lib.load_library()
     rows, d = x.shape

@@ -52,52 +52,3 @@ for name, epi, N, K, od in CASES:
             if v[0] > 0:
                 print("   tile 2 box", bx, "(start | drained | ld+math+sts | fence | store issued):", [x - v[0] for x in v])
 
-M = M0
-# ---- LayerNorm-prologue GEMM (gemm_lnt.cu) against LayerNorm kernel + GEMM
-from gpu_util import op_layernorm  # noqa: E402
-d = 512
-x = torch.randn(M, d, device="cuda")
-gam = torch.ones(d, device="cuda"); bet = torch.zeros(d, device="cuda")
-a = torch.empty(M, d, device="cuda", dtype=torch.bfloat16)
-for name, epi, N in [("lna linear1+swish", "SWISH", 2048), ("lna qkv", "QKV", 1536), ("lna pw1+glu", "GLU", 1024)]:
-    W = (torch.randn(N, d, device="cuda") / d ** 0.5).bfloat16()
-    bias = torch.randn(N, device="cuda")
-    ncols = {"QKV": N + 512, "GLU": N // 2}.get(epi, N)
-    out = torch.zeros(M, ncols, device="cuda", dtype=torch.bfloat16)
-    lens = torch.full((32,), 500, dtype=torch.int32, device="cuda")
-    def split():
-        rc = lib.cfb_op_layernorm(ptr(x), ptr(gam), ptr(bet), ptr(a), _lib.CFB_BF16, M, d, None, 1, stream())
-        assert rc == 0
-        rc = lib.cfb_op_gemm(1, EPI[epi], ptr(a), d, ptr(W), d, ptr(bias), ptr(bias), M, N, d, ptr(out), ncols, _lib.CFB_BF16, 1.0,
-                             ptr(lens) if epi == "GLU" else None, 500, 512 if epi == "QKV" else 0, None, stream())
-        assert rc == 0
-    def fused_t():
-        rc = lib.cfb_op_gemm_lnt(EPI[epi], ptr(x), d, None, None, None, ptr(gam), ptr(bet), ptr(W), d, ptr(bias), ptr(bias), M, N, d,
-                                 ptr(out), ncols, ptr(lens) if epi == "GLU" else None, 500, 512 if epi == "QKV" else 0, stream())
-        assert rc == 0, _lib.last_error(None)
-    def fused_t2():  # norm_out + next LayerNorm in the prologue (x rewritten in place)
-        rc = lib.cfb_op_gemm_lnt(EPI[epi], ptr(x), d, ptr(gam), ptr(bet), ptr(x), ptr(gam), ptr(bet), ptr(W), d, ptr(bias), ptr(bias), M, N, d,
-                                 ptr(out), ncols, ptr(lens) if epi == "GLU" else None, 500, 512 if epi == "QKV" else 0, stream())
-        assert rc == 0, _lib.last_error(None)
-    for fn, tag in ((fused_t, "fused tmem"), (fused_t2, "tmem dual"), (split, "LN + GEMM")):
-        for _ in range(3): fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20): fn()
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 20
-        print(f"{name:24s} {tag:10s}: {ms * 1e3:7.1f} us  {2.0 * M * N * d / ms / 1e9:7.0f} TFLOP/s")
-
-# ---- library reference point: torch.matmul (cuBLAS) on the same shapes, bf16 in / bf16 out, no epilogue
-if os.environ.get("CFB_BENCH_CUBLAS"):
-    for N, K in [(2048, 512), (512, 2048), (1024, 512), (512, 512)]:
-        A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16(); W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
-        for _ in range(3): torch.matmul(A, W.t())
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(20): torch.matmul(A, W.t())
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 20
-        print(f"cuBLAS bf16 M={M} N={N} K={K}: {ms * 1e3:7.1f} us  {2.0 * M * N * K / ms / 1e9:7.0f} TFLOP/s")
