@@ -417,26 +417,6 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         ptx::tmem_ld_x32(tS + 32, s1r);
         ptx::tc_wait_ld();
         if (ts) CFB_TR(16 + it * 16 + 10);
-        if (dbg & 64) {
-          // experiment: 17 aligned 16-byte loads + a two-level select network instead of 64 4-byte loads
-          const int s4 = sh & 3;
-          const uint32_t abase = shift_row + (sh & ~3) * 4;
-          float win[68];
-#pragma unroll
-          for (int q = 0; q < 17; ++q) {
-            const float4 v4 = lds_f32x4(abase + 16 * q);
-            win[4 * q] = v4.x, win[4 * q + 1] = v4.y, win[4 * q + 2] = v4.z, win[4 * q + 3] = v4.w;
-          }
-          const bool b0 = (s4 & 1) != 0, b1 = (s4 & 2) != 0;
-#pragma unroll
-          for (int c = 0; c < 66; ++c) win[c] = b0 ? win[c + 1] : win[c];
-#pragma unroll
-          for (int c = 0; c < 64; ++c) win[c] = b1 ? win[c + 2] : win[c];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) sv[c] = __uint_as_float(s0r[c]) + win[c];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) sv[32 + c] = __uint_as_float(s1r[c]) + win[32 + c];
-        } else {
         float g[32];
         if (dbg & 4) {
 #pragma unroll
@@ -449,7 +429,6 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         if (!(dbg & 4)) ptx::lds_f32x32(shift_row + sh * 4 + 128, g);
 #pragma unroll
         for (int c = 0; c < 32; ++c) sv[32 + c] = __uint_as_float(s1r[c]) + g[c];
-        }
       }
       if (ts) CFB_TR(16 + it * 16 + 2);
       if (j0 + kBN > len) {  // only the last key tile can contain masked keys
@@ -583,11 +562,6 @@ extern "C" __attribute__((visibility("default"))) int cfb_debug_attn_trace(long 
 
 int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
   if ((a.tiles == nullptr && a.B <= 0) || a.T <= 0) return 0;
-  {
-    // two threads per query row (attention_tc5.cu): CFB_ATTN_V=5 selects it (experiments)
-    const char* av = getenv("CFB_ATTN_V");
-    if (av != nullptr && atoi(av) == 5 && a.dkp == 64) return launch_attn_tc5(a, st, err);
-  }
   {
     // persistent form (attention_tcp.cu).  Measured (r02t): 256 x 100 frames x 4 heads 48.3 -> 43.3 us, 32 x 500 x 8
     // 93.3 -> 92.1 us, 1 x 7500 x 8 477 -> 504 us: it removes the per-CTA setup, which matters for short sequences; the

@@ -138,8 +138,6 @@ int launch_gemm_simt(const GemmDesc& g, float* scratch, cudaStream_t st, std::st
 int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err);
 // persistent form (one CTA per SM walks over the (query tile, head, sequence) items; attention_tcp.cu)
 int launch_attn_tcp(const AttnDesc& a, cudaStream_t st, std::string* err);
-// two threads per query row, 16 softmax warps (attention_tc5.cu)
-int launch_attn_tc5(const AttnDesc& a, cudaStream_t st, std::string* err);
 int launch_attn_simt(const AttnDesc& a, cudaStream_t st, std::string* err);
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int rows, int d,
