@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import json
 import os
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Any, Callable, Iterable, Iterator, List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -188,6 +188,12 @@ class StagedBatch:
     sample_ids: torch.Tensor              # (B,) int32 host = manifest ids
     ready: Any = None                     # torch.cuda.Event recorded after the copies (None on the host)
     slot: int = 0
+    audio_lengths_host: List[int] = field(default_factory=list)   # the same lengths as host integers (no sync to get them)
+
+    def feature_lengths_host(self, hop: int = 160) -> List[int]:
+        """Frames the preprocessor makes of every utterance (features.py:347-353), as host integers: what
+        ``ConformerEncoder.forward(..., length_host=)`` needs to run a ragged sub-batch in its packed layout."""
+        return [feature_frames(n, hop) for n in self.audio_lengths_host]
 
 
 class CollationService:
@@ -267,7 +273,7 @@ class CollationService:
                     ready = torch.cuda.Event()
                     ready.record(self._stream)
                 self._busy[slot] = ready
-            yield StagedBatch(list(idx), audio, lens, tokens, tok_lens, ids, ready, slot)
+            yield StagedBatch(list(idx), audio, lens, tokens, tok_lens, ids, ready, slot, [self.lengths[i] for i in idx])
 
     def wait(self, batch: StagedBatch, stream=None):
         """Makes ``stream`` (default: the current stream) wait for the batch's copies and tells the caching allocator that

@@ -142,7 +142,8 @@ def test_service_covers_every_utterance_once_and_bounds_padding():
             # the staged batch is a CONTIGUOUS view of its slot: the H2D copy is then one async copy from pinned memory
             assert b.audio_signal.is_contiguous()
             assert b.audio_signal.data_ptr() == svc._audio[b.slot].data_ptr()
-            assert b.audio_lengths.tolist() == [lengths[i] for i in b.indices]
+            assert b.audio_lengths.tolist() == [lengths[i] for i in b.indices] == b.audio_lengths_host
+            assert b.feature_lengths_host(160) == [n // 160 + 1 for n in b.audio_lengths_host]
             assert b.sample_ids.tolist() == b.indices
             for row, i in enumerate(b.indices):
                 assert torch.equal(b.audio_signal[row, :lengths[i]], load(i)[0])

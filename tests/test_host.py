@@ -296,3 +296,58 @@ def test_plan_shards_auto_bucket_width_trades_padding_against_launch_overhead():
             fixed = plan_shards(lengths, n, 64, width)
             assert plan_cost(lengths, auto) <= plan_cost(lengths, fixed) + 1e-6
         assert sum(len(b) for b in auto.batches) < sum(len(b) for b in plan_shards(lengths, n, 64, 128).batches)
+
+
+def test_packed_layout_host_arithmetic_and_dispatch_rule():
+    """Host side of the packed forward (no GPU): the slot arithmetic the wrapper uses to decide and to size things must
+    be the one of csrc/common.cuh (slot = T'_b + 15 rows rounded up to 8; T1 = (len + 1) >> 1, T' = (T1 + 1) >> 1 with
+    lengths clipped to [0, T]), and the dispatch rule: packed only with host lengths, bf16, no out_proj, >= 15 % saved."""
+    enc = cn.ConformerEncoder(feat_in=80, n_layers=1, d_model=64, n_heads=4)
+
+    def model(lens, t):
+        rows = 0
+        for n in lens:
+            n = min(max(n, 0), t)
+            t2 = (((n + 1) // 2) + 1) // 2
+            rows += -(-(t2 + 15) // 8) * 8
+        return rows
+
+    for lens, t in (([1000, 37, 640, 333, 5, 999, 2, 1, 0], 1000), ([2965, 271], 2965), ([400] * 7, 400), ([5000, -3], 1200)):
+        assert enc.packed_rows(lens, t) == model(lens, t)
+    assert enc.packed_rows([1000], 1000) == 272 and enc.packed_rows([0], 8) == 16
+    # a tensor of int32 T' values agrees with calc_length (subsampling.py:272-282) on the same lengths
+    lens = [1, 2, 3, 4, 5, 17, 333, 640, 900, 1000, 2001]
+    t2 = [(((n + 1) // 2) + 1) // 2 for n in lens]
+    assert t2 == oc.subsampled_lengths(torch.tensor(lens), 2).tolist()
+    assert enc._want_packed((1000, 100), 2, 1000, 250) and not enc._want_packed((1000, 990), 2, 1000, 250)
+    assert not enc._want_packed(None, 2, 1000, 250)
+    enc.packed = False
+    assert not enc._want_packed((1000, 100), 2, 1000, 250)
+    enc.packed = True
+    assert enc._want_packed((1000, 990), 2, 1000, 250)
+    assert not cn.ConformerEncoder(feat_in=80, n_layers=1, d_model=64, n_heads=4, precision="fp32_validate")._want_packed(
+        (1000, 100), 2, 1000, 250)
+    assert not cn.ConformerEncoder(feat_in=80, n_layers=1, d_model=64, n_heads=4, feat_out=32)._want_packed(
+        (1000, 100), 2, 1000, 250)
+    # graph identity: a packed capture is keyed by its lengths, a dense one is not
+    k1 = enc.graph_key(2, 1000, torch.float32, True, torch.float32, 0, (1000, 100))
+    k2 = enc.graph_key(2, 1000, torch.float32, True, torch.float32, 0, (1000, 200))
+    assert k1 != k2 and enc.graph_key(2, 1000, torch.float32, True, torch.float32, 0, None) not in (k1, k2)
+
+
+def test_one_sub_batch_per_rank_when_buckets_are_unbounded():
+    """With the packed forward padding costs nothing, so bench.py / INTEGRATION.md plan with an unbounded bucket width:
+    every rank then gets exactly one sub-batch (one launch set) and the LPT balance is untouched."""
+    import random
+
+    rnd = random.Random(1234)
+    lengths = [rnd.randint(200, 3000) for _ in range(64)]
+    for world in (1, 2, 4, 8):
+        plan = cn.plan_shards(lengths, world, bucket_frames=1 << 30)
+        assert [len(b) for b in plan.batches] == [1] * world
+        assert sorted(i for b in plan.batches for s in b for i in s) == list(range(64))
+        costs = plan.cost
+        assert max(costs) / min(costs) < 1.01
+        for b in plan.batches:  # descending lengths inside a share: the interleaved groups of the engine are balanced
+            ls = [lengths[i] for i in b[0]]
+            assert ls == sorted(ls, reverse=True)

@@ -303,7 +303,16 @@ def test_gpu_transducer_pipeline_waveform_to_hypotheses():
     for batch in svc:
         svc.wait(batch)
         feats, flen = pre(input_signal=batch.audio_signal, length=batch.audio_lengths)
-        encoded, elen = enc(audio_signal=feats, length=flen)
+        # the service knows the lengths on the host: ragged sub-batches take the packed forward, which must equal the dense one
+        enc.packed = False
+        dense, dense_len = enc(audio_signal=feats, length=flen)
+        dense = dense.clone()
+        enc.packed = "auto"
+        assert batch.feature_lengths_host() == flen.cpu().tolist()
+        encoded, elen = enc(audio_signal=feats, length=flen, length_host=batch.feature_lengths_host())
+        assert torch.equal(elen, dense_len)
+        for row, n in enumerate(elen.cpu().tolist()):
+            assert torch.equal(encoded[row, :, :n], dense[row, :, :n])
         (hyps,) = greedy(encoder_output=encoded, encoded_lengths=elen)
         want = ro.rnnt_greedy_decode(encoded.float().cpu(), elen.cpu(), dec_sd, joint_sd, 10, "relu", False)
         assert _compare(hyps, want) == []
