@@ -587,6 +587,13 @@ def run_b200(args):
         s_batches, s_audio, _, s_cfg = build_batches(args, kw, rank, world, name="cfg3")
         sm = measure_workload(enc, args, s_batches, s_audio, device, barrier, max_over_ranks, None, eager=False)
         stats = packing_stats(enc, s_batches)
+        # algorithmic FLOPs of THIS rank's share (valid frames only) against the step time: how far the
+        # share is from the tensor peak once padding is gone -- the rest is the fixed cost of ~250 dependent launches
+        fl_s, _ = algorithmic_costs(kw, [ln.tolist() for _, ln in s_batches])
+        share_tflop = sum(v for k, v in fl_s.items()) / 1e12
+        stats.update(algorithmic_tflop=round(share_tflop, 4),
+                     achieved_tflops=round(share_tflop / (sm["ms_per_step"] / 1e3), 1),
+                     frac_of_sustained_peak=round(share_tflop / (sm["ms_per_step"] / 1e3) / peaks()["tflops"], 4))
         strong = {"workload": workload_config("cfg3", world)["workload"], "metric": METRIC, "unit": UNIT,
                   "value": sm["value"], "ms_per_step": sm["ms_per_step"], "n_gpus": world, "steps": args.steps,
                   "scaling": "strong", "audio_sec_per_step": s_audio, "e2e": sm["e2e"],

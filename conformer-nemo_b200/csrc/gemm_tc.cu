@@ -400,7 +400,14 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
     if (err) *err = "gemm_tc: K and leading dimensions must be multiples of 8 (16-byte TMA strides)";
     return -1;
   }
-  {
+  const int m_tiles = (g.M + kBlockM - 1) / kBlockM;
+  // Small M (a rank's share of a sharded batch, one of its groups): when 128-wide tiles still fit in one wave, every CTA
+  // owns ONE tile and its time is fill + K loop + epilogue in series -- 128-wide tiles double the CTAs and halve both the
+  // operand bytes per k-block and the epilogue per CTA (the tiles are latency-bound there, not operand-bound).  This
+  // also takes precedence over the CTA-pair kernel, whose 256 x 256 tiles are the coarsest.  CFB_GEMM_SMALL_BN=0 disables.
+  static const bool small_bn_on = !(getenv("CFB_GEMM_SMALL_BN") != nullptr && atoi(getenv("CFB_GEMM_SMALL_BN")) == 0);
+  const bool small_m = small_bn_on && g.N % 256 == 0 && 2 * m_tiles * (g.N / 256) <= num_sms();
+  if (!small_m) {
     // CTA pairs (gemm_tc2.cu): CFB_GEMM_2CTA=0 never, =1 whenever the shape allows, unset = the measured default
     const char* v2 = getenv("CFB_GEMM_2CTA");
     const int mode = v2 ? atoi(v2) : -1;
@@ -408,18 +415,10 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
     // (its MUFU-bound epilogue takes over), pw1+glu 21.3 -> 22.1, K = 2048 neutral
     if (mode != 0 && gemm_tc2_supported(g) && (mode == 1 || (g.K <= 1024 && g.N >= 1536))) return launch_gemm_tc2(g, st, err);
   }
-  // tile width: 256 for wide outputs when it does not hurt the wave count, else 128
-  const int m_tiles = (g.M + kBlockM - 1) / kBlockM;
-  // 256-wide tiles halve the re-reads of A (the kernel is bound by L2->SM bandwidth, not by the tensor pipe)
+  // tile width: 256 for wide outputs (256-wide tiles halve the re-reads of A: the kernel is bound by L2->SM bandwidth,
+  // not by the tensor pipe), else 128
   int bn = 128;
-  if (g.N % 256 == 0) bn = 256;
-  {
-    // Small M (a rank's share of a sharded batch): 256-wide tiles of an N = 512 GEMM occupy a third of the machine and
-    // each runs the whole K loop; 128-wide tiles double the CTAs and shorten the critical path (the tiles are
-    // latency-bound there, not operand-bound).  CFB_GEMM_SMALL_BN=0 keeps 256.
-    static const bool small_bn = !(getenv("CFB_GEMM_SMALL_BN") != nullptr && atoi(getenv("CFB_GEMM_SMALL_BN")) == 0);
-    if (small_bn && bn == 256 && 2 * m_tiles * (g.N / 256) <= num_sms()) bn = 128;
-  }
+  if (g.N % 256 == 0 && !small_m) bn = 256;
   const int n_tiles = (g.N + bn - 1) / bn;
 
   CUtensorMap tmA, tmB;
