@@ -1,0 +1,5 @@
+#!/bin/bash
+# fused residual GEMM + LayerNorm: parity, then timing against the two-kernel path
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_gemm_ln.py -x -q 2>&1 | tail -15 > gpurun_out/r6a_test_gemm_ln.log; cat gpurun_out/r6a_test_gemm_ln.log
+timeout 300 python tools/bench_gemm_ln.py > gpurun_out/r6a_bench_gemm_ln.log 2>&1; cat gpurun_out/r6a_bench_gemm_ln.log
