@@ -23,7 +23,7 @@ STATUS_NAMES = {1: "invalid argument", 2: "unsupported configuration", 3: "missi
 SYMBOLS = [
     "cfb_create", "cfb_destroy", "cfb_last_error", "cfb_set_weight", "cfb_finalize_weights", "cfb_output_frames",
     "cfb_workspace_bytes", "cfb_forward", "cfb_packed_workspace_bytes", "cfb_forward_packed", "cfb_debug_buffer", "cfb_set_profiling", "cfb_profile_report",
-    "cfb_last_launch_count", "cfb_op_gemm", "cfb_op_gemm_ln", "cfb_op_ctc_head", "cfb_ctc_head_scratch_bytes", "cfb_op_ctc_collapse",
+    "cfb_last_launch_count", "cfb_op_gemm", "cfb_op_ctc_head", "cfb_ctc_head_scratch_bytes", "cfb_op_ctc_collapse",
     "cfb_op_layernorm", "cfb_op_depthwise", "cfb_op_dw_pw2", "cfb_op_logmel", "cfb_op_rel_attention", "cfb_op_lengths",
     "cfb_rnnt_greedy_scratch_bytes", "cfb_op_rnnt_greedy",
 ]
@@ -83,7 +83,6 @@ def load_library() -> ctypes.CDLL:
         lib.cfb_profile_report.argtypes = [vp, ctypes.c_char_p, sz]
         lib.cfb_op_gemm.argtypes = [i32, i32, vp, i64, vp, i64, vp, vp, i32, i32, i32, vp, i64, i32, ctypes.c_float,
                                     vp, i32, i32, vp, vp]
-        lib.cfb_op_gemm_ln.argtypes = [vp, i64, vp, i64, vp, ctypes.c_float, vp, i64, vp, vp, vp, vp, i32, i32, i32, vp, i64, vp]
         lib.cfb_ctc_head_scratch_bytes.argtypes = [i32, i32, i32]
         lib.cfb_op_ctc_head.argtypes = [vp, i32, vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]
         lib.cfb_op_ctc_collapse.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]

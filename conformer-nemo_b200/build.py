@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(LIB_DIR, "libcfb.so")
 
-SOURCES = ["engine.cu", "tmap.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_lnc.cu", "gemm_simt.cu", "elementwise.cu", "packed.cu", "conv_tail.cu", "attention_tc.cu", "attention_tcp.cu",
+SOURCES = ["engine.cu", "tmap.cu", "gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "elementwise.cu", "packed.cu", "conv_tail.cu", "attention_tc.cu", "attention_tcp.cu",
            "attention_simt.cu", "ctc_head.cu", "frontend.cu", "rnnt_greedy.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

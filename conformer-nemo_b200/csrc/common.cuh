@@ -133,27 +133,6 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err);
 bool gemm_tc2_supported(const GemmDesc& g);
 int launch_gemm_tc2(const GemmDesc& g, cudaStream_t st, std::string* err);
 long long* g_gemm_trace_view();
-// residual GEMM with the following LayerNorm(s) in its epilogue, row-complete across a CTA pair (gemm_lnc.cu):
-//   v = x + alpha * (A W^T + bias);  y = LN1(v) if gamma1 else v;  x <- y (fp32, in place);  out_bf16 <- LN2(y)
-struct GemmLnDesc {
-  const void* A = nullptr;
-  long long lda = 0;
-  const void* W = nullptr;
-  long long ldw = 0;
-  int M = 0, N = 0, K = 0;
-  const float* bias = nullptr;
-  float alpha = 1.f;
-  float* x = nullptr;  // (M x N) fp32 residual stream, read and rewritten
-  long long ldx = 0;
-  const float* gamma1 = nullptr;  // optional LayerNorm applied to the stream itself (norm_out)
-  const float* beta1 = nullptr;
-  const float* gamma2 = nullptr;  // LayerNorm of the bf16 output (the next block's input normalisation)
-  const float* beta2 = nullptr;
-  void* out_bf16 = nullptr;
-  long long ldo = 0;
-};
-bool gemm_lnc_supported(int M, int N, int K);
-int launch_gemm_lnc(const GemmLnDesc& g, cudaStream_t st, std::string* err);
 int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err);
 int launch_gemm_simt(const GemmDesc& g, float* scratch, cudaStream_t st, std::string* err);
 int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err);

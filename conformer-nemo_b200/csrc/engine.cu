@@ -776,37 +776,6 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     fused_tail = ctas * 100 >= waves * sms * 65;
   }
 
-  // Residual GEMM + the following LayerNorm(s) in one kernel (gemm_lnc.cu): linear2 of the first feed-forward + norm_self_att,
-  // linear_out + norm_conv, linear2 of the second feed-forward + norm_out + the next layer's norm_feed_forward1.
-  // CFB_FUSED_LN=0 keeps the stand-alone LayerNorm kernels.
-  const char* fln_var = getenv("CFB_FUSED_LN");
-  const bool fused_ln = !v && gemm_lnc_supported(N, d, d) && (fln_var != nullptr ? atoi(fln_var) != 0 : true);
-  auto gemm_ln = [&](const void* A, long long lda, const Slot& W, int K, const Slot& bias, float alpha, const float* g1,
-                     const float* b1, const float* g2, const float* b2, const char* what) -> int {
-    GemmLnDesc g;
-    g.A = A;
-    g.lda = lda;
-    g.W = h->arena + W.off;
-    g.ldw = K;
-    g.M = N;
-    g.N = d;
-    g.K = K;
-    g.bias = h->at<float>(bias);
-    g.alpha = alpha;
-    g.x = reinterpret_cast<float*>(ws + pl.x);
-    g.ldx = d;
-    g.gamma1 = g1;
-    g.beta1 = b1;
-    g.gamma2 = g2;
-    g.beta2 = b2;
-    g.out_bf16 = ws + pl.a;
-    g.ldo = d;
-    int rc = launch_gemm_lnc(g, st, &err);
-    launches += 1;
-    if (rc != 0 && err.empty()) err = what;
-    return rc;
-  };
-
   // ---- lengths (subsampling.py:164-171)
   if (!pk || pk->prologue) {
     CFB_TRY(launch_lengths(reinterpret_cast<const long long*>(lengths), encoded_len, B, T, 2, st), "lengths");
@@ -899,11 +868,9 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     for (int f = 0; f < 2; ++f) {
       if (f == 1) {
         // -- self attention (conformer_modules.py:103-110)
-        if (!fused_ln) {  // otherwise written by the first feed-forward's linear2
-          CFB_TRY(launch_layernorm(x, h->at<float>(lw.ln_g[1]), h->at<float>(lw.ln_b[1]), a, abf, N, d, nullptr, 1, st),
-                  "norm_self_att");
-          ++launches;
-        }
+        CFB_TRY(launch_layernorm(x, h->at<float>(lw.ln_g[1]), h->at<float>(lw.ln_b[1]), a, abf, N, d, nullptr, 1, st),
+                "norm_self_att");
+        ++launches;
         EpiParams ep;
         ep.bias = h->at<float>(lw.b_qkv);
         ep.bias2 = h->at<float>(lw.b_qv);
@@ -934,17 +901,11 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
         eo.out = x;
         eo.ldo = d;
         eo.alpha = 1.f;
-        if (fused_ln) {
-          CFB_TRY(gemm_ln(ws + pl.ctx, Dp, lw.w_out, Dp, lw.b_out, 1.f, nullptr, nullptr, h->at<float>(lw.ln_g[2]),
-                          h->at<float>(lw.ln_b[2]), "linear_out"),
-                  "linear_out");
-        } else {
         CFB_TRY(gemm(ws + pl.ctx, Dp, lw.w_out, Dp, N, d, Dp, EPI_RESID, false, eo, "linear_out"), "linear_out");
         // -- convolution module (conformer_modules.py:112-114, 160-180)
         CFB_TRY(launch_layernorm(x, h->at<float>(lw.ln_g[2]), h->at<float>(lw.ln_b[2]), a, abf, N, d, nullptr, 1, st),
                 "norm_conv");
         ++launches;
-        }
         EpiParams eg;
         eg.bias = h->at<float>(lw.b_pw1);
         eg.out = ws + pl.g;
@@ -998,22 +959,10 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
       e2.out = x;
       e2.ldo = d;
       e2.alpha = 0.5f;  // fc_factor (conformer_modules.py:57,101,118)
-      if (fused_ln && f == 0) {
-        CFB_TRY(gemm_ln(ws + pl.hbuf, dff, lw.ff_w2[f], dff, lw.ff_b2[f], 0.5f, nullptr, nullptr, h->at<float>(lw.ln_g[1]),
-                        h->at<float>(lw.ln_b[1]), "linear2"),
-                "linear2");
-      } else if (fused_ln && l + 1 < L) {
-        const LayerW& nx = h->layers[l + 1];
-        CFB_TRY(gemm_ln(ws + pl.hbuf, dff, lw.ff_w2[f], dff, lw.ff_b2[f], 0.5f, h->at<float>(lw.ln_g[4]),
-                        h->at<float>(lw.ln_b[4]), h->at<float>(nx.ln_g[0]), h->at<float>(nx.ln_b[0]), "linear2"),
-                "linear2");
-      } else {
       CFB_TRY(gemm(ws + pl.hbuf, dff, lw.ff_w2[f], dff, N, d, dff, EPI_RESID, false, e2, "linear2"), "linear2");
-      }
     }
     // -- norm_out (conformer_modules.py:120); the last one writes the result
     const bool last = (l == L - 1);
-    if (fused_ln && !last) continue;  // norm_out and the next norm_feed_forward1 left with the second linear2
     if (last && pk) {
       // the dense (B, T', d) result of the reference API: zeros, then the valid rows of every slot (packed.cu)
       if (pk->prologue) {
@@ -1236,32 +1185,6 @@ int cfb_op_gemm(int use_tc, int epilogue, const void* A, int64_t lda, const void
   std::string err;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = use_tc ? launch_gemm_tc(g, st, &err) : launch_gemm_simt(g, scratch, st, &err);
-  return rc == 0 ? CFB_OK : op_fail(rc, err);
-}
-
-int cfb_op_gemm_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float alpha, float* x,
-                   int64_t ldx, const float* gamma1, const float* beta1, const float* gamma2, const float* beta2, int M,
-                   int N, int K, void* out_bf16, int64_t ldo, cfb_stream stream) {
-  GemmLnDesc g;
-  g.A = A;
-  g.lda = lda;
-  g.W = W;
-  g.ldw = ldw;
-  g.M = M;
-  g.N = N;
-  g.K = K;
-  g.bias = bias;
-  g.alpha = alpha;
-  g.x = x;
-  g.ldx = ldx;
-  g.gamma1 = gamma1;
-  g.beta1 = beta1;
-  g.gamma2 = gamma2;
-  g.beta2 = beta2;
-  g.out_bf16 = out_bf16;
-  g.ldo = ldo;
-  std::string err;
-  int rc = launch_gemm_lnc(g, reinterpret_cast<cudaStream_t>(stream), &err);
   return rc == 0 ? CFB_OK : op_fail(rc, err);
 }
 

@@ -160,17 +160,6 @@ CFB_API int cfb_op_gemm(int use_tensor_cores, int epilogue, const void* A, int64
                 float alpha, const int32_t* lens, int frames_per_seq, int qkv_dp, float* scratch,
                 cfb_stream stream);
 
-/* Residual GEMM with the following LayerNorm(s) fused into its epilogue (tcgen05 path only; N <= 512, N % 8 == 0):
- *   v = x + alpha * (A W^T + bias)                                      conformer_modules.py:98-118 (residual updates)
- *   y = LayerNorm(v; gamma1, beta1) if gamma1 != NULL else v            (norm_out, :120)
- *   x (M x N fp32, ldx) <- y, in place
- *   out_bf16 (M x N bf16, ldo) <- LayerNorm(y; gamma2, beta2)           (the next block's input norm, :98/:103/:112)
- * Replaces cfb_op_gemm(CFB_EPI_RESID) + cfb_op_layernorm: N > 256 runs on pairs of CTAs that own 256 columns each and
- * exchange the row statistics through distributed shared memory. */
-CFB_API int cfb_op_gemm_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float alpha, float* x,
-                   int64_t ldx, const float* gamma1, const float* beta1, const float* gamma2, const float* beta2, int M,
-                   int N, int K, void* out_bf16, int64_t ldo, cfb_stream stream);
-
 /* y = LayerNorm(x) * gamma + beta over the last dim (eps 1e-5; conformer_modules.py:60-86). x fp32 (rows x d);
  * out_dtype CFB_BF16 / CFB_F32.  lens != NULL: rows at frames >= lens[seq] are written as zeros. */
 CFB_API int cfb_op_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_dtype, int rows,

@@ -31,18 +31,6 @@ def op_gemm(use_tc, epi, A, W, bias=None, bias2=None, out=None, alpha=1.0, lens=
     return out
 
 
-def op_gemm_ln(A, W, bias, alpha, x, ln1, ln2, out_bf16):
-    """Residual GEMM + fused LayerNorm(s) (cfb_op_gemm_ln): x (M, N) fp32 updated in place; ln1 / ln2: (gamma, beta)."""
-    lib = _lib.load_library()
-    M, K = A.shape
-    N = W.shape[0]
-    g1, b1 = ln1 if ln1 is not None else (None, None)
-    rc = lib.cfb_op_gemm_ln(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), float(alpha), ptr(x), x.stride(0), ptr(g1),
-                            ptr(b1), ptr(ln2[0]), ptr(ln2[1]), M, N, K, ptr(out_bf16), out_bf16.stride(0), stream())
-    assert rc == 0, _lib.last_error(None)
-    torch.cuda.synchronize()
-
-
 def op_layernorm(x, gamma, beta, out, lens=None, frames_per_seq=1):
     lib = _lib.load_library()
     rows, d = x.shape
