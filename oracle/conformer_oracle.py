@@ -49,6 +49,7 @@ class EncoderConfig:
     n_heads: int = 8
     xscaling: bool = True
     conv_kernel_size: int = 31
+    untie_biases: bool = True  # False: one (pos_bias_u, pos_bias_v) pair shared by every layer (conformer_encoder.py:165-173)
 
     @property
     def conv_channels(self) -> int:
@@ -301,6 +302,12 @@ def random_state_dict(cfg: EncoderConfig, seed: int = 0) -> Dict[str, Tensor]:
                     fan_in *= s
             bound = 1.0 / math.sqrt(fan_in)
             sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    if not cfg.untie_biases:
+        # the shared pair is a local of the reference constructor, not an attribute (conformer_encoder.py:165-173): the
+        # state_dict lists it under every layer's name, all with the same values
+        for name in ("pos_bias_u", "pos_bias_v"):
+            for i in range(1, cfg.n_layers):
+                sd[f"layers.{i}.self_attn.{name}"] = sd[f"layers.0.self_attn.{name}"].clone()
     return sd
 
 

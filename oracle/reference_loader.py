@@ -108,6 +108,7 @@ def build_reference_encoder(cfg, state_dict=None):
         subsampling_conv_channels=cfg.subsampling_conv_channels, ff_expansion_factor=cfg.ff_expansion_factor,
         self_attention_model="rel_pos", n_heads=cfg.n_heads, xscaling=cfg.xscaling,
         conv_kernel_size=cfg.conv_kernel_size, dropout=0.1, dropout_emb=0.0, dropout_att=0.1,
+        untie_biases=getattr(cfg, "untie_biases", True),
     )
     if state_dict is not None:
         missing, unexpected = enc.load_state_dict(state_dict, strict=False)

@@ -35,6 +35,13 @@ CASES = {
     "noxscale_d64": (dict(feat_in=80, n_layers=1, d_model=64, n_heads=4, xscaling=False), 6, 2, 50, [50, 1], False),
     # full depth of the Large recipes (conformer_transducer_bpe.yaml:110), small B / T: pins the oracle's drift over 17 layers
     "large17_d512": (dict(feat_in=80, n_layers=17, d_model=512, n_heads=8), 7, 2, 300, [300, 173], False),
+    # constructor variants no other case reaches: shorter depth-wise kernels (taps centred in the 31-tap window), feed-forward
+    # expansion factors other than 4, and the tied (encoder-level) pos_bias_u / pos_bias_v pair of untie_biases=False
+    "k15_ff2_d64": (dict(feat_in=80, n_layers=2, d_model=64, n_heads=4, conv_kernel_size=15, ff_expansion_factor=2), 8, 2, 90,
+                    [90, 41], False),
+    "k9_ff8_d176": (dict(feat_in=80, n_layers=1, d_model=176, n_heads=4, conv_kernel_size=9, ff_expansion_factor=8), 9, 2, 120,
+                    [120, 77], False),
+    "tied_d256": (dict(feat_in=80, n_layers=3, d_model=256, n_heads=4, untie_biases=False), 10, 2, 130, [130, 64], False),
 }
 
 

@@ -33,7 +33,7 @@ def build(cfg: oc.EncoderConfig, sd, precision):
     enc = cn.ConformerEncoder(feat_in=cfg.feat_in, n_layers=cfg.n_layers, d_model=cfg.d_model, feat_out=cfg.feat_out,
                               subsampling_conv_channels=cfg.subsampling_conv_channels,
                               ff_expansion_factor=cfg.ff_expansion_factor, n_heads=cfg.n_heads, xscaling=cfg.xscaling,
-                              conv_kernel_size=cfg.conv_kernel_size, precision=precision)
+                              conv_kernel_size=cfg.conv_kernel_size, untie_biases=cfg.untie_biases, precision=precision)
     missing, unexpected = enc.load_state_dict(sd, strict=False)
     assert not unexpected and all("num_batches_tracked" in m for m in missing), (missing, unexpected)
     return enc.cuda().eval()

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 def build(cfg, sd):
     enc = cn.ConformerEncoder(feat_in=cfg.feat_in, n_layers=cfg.n_layers, d_model=cfg.d_model, n_heads=cfg.n_heads,
-                              conv_kernel_size=cfg.conv_kernel_size)
+                              conv_kernel_size=cfg.conv_kernel_size, untie_biases=cfg.untie_biases)
     enc.load_state_dict(sd, strict=False)
     return enc.cuda().eval()
 

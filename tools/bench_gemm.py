@@ -47,6 +47,9 @@ for name, epi, N, K, od in CASES:
         buf = (ctypes.c_longlong * 128)()
         lib.cfb_debug_gemm_trace(buf)
         t = list(buf)
+        if not any(v > 0 for v in t):
+            print("   (no trace: the CTA-pair kernel ran; CFB_GEMM_2CTA=0 forces the traced single-CTA kernel)")
+            continue
         base = min(v for v in t if v > 0)
         ep = [(t[i * 4] - base, t[i * 4 + 1] - base, t[i * 4 + 2] - base) for i in range(8) if t[i * 4] > 0]
         mm = [(t[64 + i * 4] - base, t[64 + i * 4 + 1] - base, t[64 + i * 4 + 2] - base) for i in range(8) if t[64 + i * 4] > 0]
