@@ -704,6 +704,15 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
   size_t prof_e0 = 0;
   const char* prof_label = nullptr;
   // NVTX: one range per launch group, named like the profile report's labels (nsys / ncu --nvtx group kernels by them)
+  // Under stream capture the brackets become event-record NODES of the graph (cudaEventRecordExternal): every replay
+  // re-records them on the GPU's own timeline, so the intervals hold the kernel and the node-to-node launch latency the
+  // replayed step really pays, but none of the host's enqueue cost (eager brackets around a 5 us kernel measure mostly
+  // how fast the host enqueues: the GPU runs ahead of it).
+  unsigned int ev_flags = cudaEventRecordDefault;
+  if (h->profiling) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) ev_flags = cudaEventRecordExternal;
+  }
   auto tick = [&](const char* label) {
     nvtxRangePushA(label);
     if (!h->profiling) return;
@@ -713,13 +722,13 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     }
     prof_label = label;
     prof_e0 = h->ev_used++;
-    cudaEventRecord(h->ev_pool[prof_e0], st);
+    cudaEventRecordWithFlags(h->ev_pool[prof_e0], st, ev_flags);
   };
   auto tock = [&]() {
     nvtxRangePop();
     if (!h->profiling || !prof_label) return;
     const size_t e1 = h->ev_used++;
-    cudaEventRecord(h->ev_pool[e1], st);
+    cudaEventRecordWithFlags(h->ev_pool[e1], st, ev_flags);
     h->recs.push_back({prof_label, prof_e0, e1});
     prof_label = nullptr;
   };
@@ -776,6 +785,12 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     fused_tail = ctas * 100 >= waves * sms * 65;
   }
 
+  // calibration of the brackets themselves: two event records with nothing between them (reported under this label; a
+  // bracket around a kernel holds the same fixed cost on top of the kernel's launch latency and run time)
+  if (h->profiling) {
+    tick("(empty bracket)");
+    tock();
+  }
   // ---- lengths (subsampling.py:164-171)
   if (!pk || pk->prologue) {
     CFB_TRY(launch_lengths(reinterpret_cast<const long long*>(lengths), encoded_len, B, T, 2, st), "lengths");
