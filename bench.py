@@ -250,6 +250,111 @@ GEMM_LABELS = ["pre_encode.out", "linear_pos", "qkv projection", "linear_out", "
                "linear1+swish", "linear2"]  # the fused depthwise+pointwise_conv2 kernel is not gemm_tc_kernel: reported apart
 
 
+def measure_pipelines(enc, device, steps=5, warmup=2, batch=32, seconds=20):
+    """The widened rows composed around the SAME encoder: pinned host waveforms ->
+    log-mel kernels -> encoder (graph replay) -> (a) CTC head + greedy collapse, (b) transducer greedy decode -> token ids
+    on the host.  Random-init heads of the recipes' sizes (the modules' own initialisers), blank biases calibrated so that
+    both decoders emit a speech-like 0.2 symbols per encoder frame.  Wall clock over whole batches, everything included."""
+    import conformer_nemo_b200 as cn
+
+    n_samp = seconds * 16000
+    audio = (torch.randn(batch, n_samp, generator=torch.Generator().manual_seed(0)) * 0.1).pin_memory()
+    lengths = torch.full((batch,), n_samp, dtype=torch.int64).pin_memory()
+    vocab = 1024
+    torch.manual_seed(0)
+    pre = cn.AudioToMelSpectrogramPreprocessor(window_size=0.025, window_stride=0.01, features=80, n_fft=512, pad_to=0).to(device)
+    head = cn.ConvASRDecoder(feat_in=enc._feat_out, num_classes=vocab).to(device)
+    dec = cn.RNNTDecoder(prednet=dict(pred_hidden=640, pred_rnn_layers=1, dropout=0.1), vocab_size=vocab).to(device)
+    joint = cn.RNNTJoint(jointnet=dict(encoder_hidden=enc._feat_out, pred_hidden=640, joint_hidden=640, activation="relu",
+                                       dropout=0.1), num_classes=vocab).to(device)
+    enc.enable_cuda_graphs(True)
+
+    def front(a, n):
+        feats, flen = pre(input_signal=a, length=n, check_lengths=False)
+        return enc(audio_signal=feats, length=flen)
+
+    encoded, elen = front(audio.to(device), lengths.to(device))
+    encoded, elen = encoded.clone(), elen.clone()
+    frames = int(elen.sum())
+    head_bias = head.decoder_layers[0].bias
+    out_bias = joint.joint_net[-1].bias
+    base_h, base_j = float(head_bias.detach()[vocab]), float(out_bias.detach()[vocab])
+
+    def ctc_rate(b):
+        with torch.no_grad():
+            head_bias[vocab] = base_h + b
+        head._invalidate()  # the packed bf16 copy of the head's weights is rebuilt from the edited bias
+        _, pred = head.forward_with_predictions(encoded)
+        return sum(len(t) for t in cn.ctc_greedy_decode(pred, elen, vocab)) / frames
+
+    lo, hi = 0.0, 8.0
+    for _ in range(10):
+        mid = 0.5 * (lo + hi)
+        lo, hi = (mid, hi) if ctc_rate(mid) > 0.2 else (lo, mid)
+    ctc_symbols = ctc_rate(hi)
+
+    greedy = cn.GreedyBatchedRNNTInfer(dec, joint, vocab, 30)
+
+    def rnnt_rate(b):
+        with torch.no_grad():
+            out_bias[vocab] = base_j + b
+        greedy.invalidate()
+        arr = greedy.decode_arrays(encoded, elen, max_tokens=30 * encoded.shape[2])
+        return arr["n_tokens"].float().sum().item() / frames
+
+    lo, hi = 0.0, 8.0
+    for _ in range(10):
+        mid = 0.5 * (lo + hi)
+        lo, hi = (mid, hi) if rnnt_rate(mid) > 0.2 else (lo, mid)
+    rnnt_symbols = rnnt_rate(hi)
+
+    def run_ctc():
+        y, yl = front(audio.to(device, non_blocking=True), lengths.to(device, non_blocking=True))
+        _, pred = head.forward_with_predictions(y)
+        return cn.ctc_greedy_decode(pred, yl, vocab)
+
+    def run_rnnt():
+        y, yl = front(audio.to(device, non_blocking=True), lengths.to(device, non_blocking=True))
+        return greedy(encoder_output=y, encoded_lengths=yl)[0]
+
+    res = {}
+    for name, fn in (("waveform_to_ctc_ids", run_ctc), ("waveform_to_transducer_hypotheses", run_rnnt)):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / steps * 1e3
+        res[name] = {"value": round(batch * seconds / (ms * 1e-3), 1), "unit": UNIT, "ms_per_batch": round(ms, 3)}
+    names = ["h2d_audio", "log_mel", "encoder", "ctc_head", "transducer_greedy_decode"]
+    best = {k: float("inf") for k in names}
+    for _ in range(3):  # device time of every stage (CUDA events), best of three passes
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        a, n = audio.to(device, non_blocking=True), lengths.to(device, non_blocking=True)
+        ev[1].record()
+        feats, flen = pre(input_signal=a, length=n, check_lengths=False)
+        ev[2].record()
+        y, yl = enc(audio_signal=feats, length=flen)
+        ev[3].record()
+        head.forward_with_predictions(y)
+        ev[4].record()
+        greedy.decode_arrays(y, yl)
+        ev[5].record()
+        torch.cuda.synchronize()
+        for i, k in enumerate(names):
+            best[k] = min(best[k], ev[i].elapsed_time(ev[i + 1]))
+    res["stage_ms"] = {k: round(v, 4) for k, v in best.items()}
+    res["config"] = {"workload": f"{batch} x {seconds} s of 16 kHz audio in pinned host memory; log-mel 80; this encoder; CTC head "
+                                 f"{vocab + 1} classes | transducer decoder / joint 640 / 640 / {vocab + 1}, max_symbols 30; ids on the host",
+                     "ctc_symbols_per_frame": round(ctc_symbols, 4), "transducer_symbols_per_frame": round(rnnt_symbols, 4),
+                     "h2d_bytes_per_batch": batch * n_samp * 4 + batch * 8, "steps": steps}
+    return res
+
+
 def _pin(t):
     return t.pin_memory() if torch.cuda.is_available() else t  # the reference arm also runs on GPU-less hosts
 
@@ -681,6 +786,13 @@ def run_b200(args):
         cpu_baseline = time_cpu_arm(kw, {k: v.detach().float().cpu() for k, v in enc.state_dict().items()},
                                     [(x, ln) for x, ln in host_batches], warmup=1, steps=2, budget_s=60.0)
 
+    pipelines = None
+    if rank == 0 and world == 1 and args.pipelines and args.workload == "cfg2":
+        try:
+            pipelines = measure_pipelines(enc, device)
+        except Exception as e:  # noqa: BLE001 -- an extra record must never cost the headline
+            pipelines = {"unavailable": f"{type(e).__name__}: {e}"}
+
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -698,6 +810,7 @@ def run_b200(args):
         "gpu_launches": launches_per_step * args.steps,
         "launch_mode": "eager" if args.no_graphs else "cuda graph replay", "eager_ms_per_step": head["eager_ms_per_step"],
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "strong": strong,
+        "pipelines": pipelines,
     }
     emit(line)
 
@@ -832,6 +945,8 @@ def main():
     ap.add_argument("--packed", default="auto", choices=["auto", "on", "off"],
                     help="variable-length layout (cfb_forward_packed) for mixed-length batches: auto = when it saves >= 15 %% "
                          "of the token rows, off = dense padded sub-batches")
+    ap.add_argument("--no-pipelines", dest="pipelines", action="store_false",
+                    help="skip the waveform -> token ids records (log-mel + encoder + CTC head / transducer decode) of the cfg2 line")
     ap.add_argument("--no-strong", dest="strong", action="store_false",
                     help="skip the cfg3 strong-scaling sub-record of the default (cfg2) line")
     ap.add_argument("--no-strong-sim", dest="strong_sim", action="store_false",
