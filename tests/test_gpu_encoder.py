@@ -402,3 +402,38 @@ def test_forward_many_runs_sub_batches_concurrently_and_bit_identically():
             assert torch.equal(yl, wl) and float((y - w).abs().max()) == 0.0
     workspaces = {e[5].data_ptr() for e in enc._graphs.values()}
     assert len(workspaces) == len(enc._graphs) == 4  # one private workspace per captured shape
+
+
+def test_profile_report_from_eager_brackets_and_from_graph_nodes():
+    """cfb_set_profiling brackets every launch with CUDA events; captured in a graph the brackets become event-record nodes
+    that every replay re-records (what bench.py's per-kernel table is read from).  Both forms list the same launches, the
+    calibration bracket around nothing included, and leave the result untouched."""
+    z, cfg, sd = load_case("tiny_d64")
+    enc = build(cfg, sd, "bf16")
+    x = torch.from_numpy(z["audio_signal"]).cuda()
+    length = torch.from_numpy(z["length"]).cuda()
+    y0, _ = enc(audio_signal=x, length=length)
+    y0 = y0.clone()
+    enc.set_profiling(True)
+    y1, _ = enc(audio_signal=x, length=length)
+    eager = enc.profile_report()
+    assert "(empty bracket)" in eager and eager["(empty bracket)"][0] == 1
+    for label in ("subsample conv 2", "linear1+swish", "linear2", "rel-pos attention", "norm_out"):
+        assert label in eager and eager[label][1] > 0.0, (label, eager)
+    assert eager["linear2"][0] == 2 * cfg.n_layers and eager["rel-pos attention"][0] == cfg.n_layers
+    assert torch.equal(y1, y0)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        enc.set_profiling(True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            y2, _ = enc(audio_signal=x, length=length)
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+        nodes = enc.profile_report()
+    enc.set_profiling(False)
+    assert {k: v[0] for k, v in nodes.items()} == {k: v[0] for k, v in eager.items()}
+    assert all(v[1] > 0.0 for v in nodes.values())
+    assert torch.equal(y2, y0)
