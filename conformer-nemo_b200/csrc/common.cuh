@@ -133,6 +133,7 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err);
 bool gemm_tc2_supported(const GemmDesc& g);
 int launch_gemm_tc2(const GemmDesc& g, cudaStream_t st, std::string* err);
 long long* g_gemm_trace_view();
+long long* gemm_trace_buffer(cudaStream_t st);
 int launch_conv_tc(const ConvDesc& c, cudaStream_t st, std::string* err);
 int launch_gemm_simt(const GemmDesc& g, float* scratch, cudaStream_t st, std::string* err);
 int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err);

@@ -354,7 +354,11 @@ int launch_instance(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     }
     configured[dev & 63] = true;
   }
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (const char* cap = getenv("CFB_GEMM_MAX_CTAS")) {  // timing experiments: fewer CTAs share the L2 (per-tile clocks via CFB_GEMM_TRACE)
+    const int c = atoi(cap);
+    if (c > 0 && c < grid) grid = c;
+  }
   cudaError_t e = launch_pdl(kern, dim3(grid), dim3(kThreads), L::kTotal, st, tmA, tmB, tmO, p);
   if (e != cudaSuccess) {
     if (err) *err = std::string("gemm_tc launch: ") + cudaGetErrorString(e);
@@ -393,6 +397,13 @@ int dispatch_epi(int epi, bool out_bf16, const CUtensorMap& tmA, const CUtensorM
 }  // namespace
 
 long long* g_gemm_trace_view() { return g_gemm_trace; }
+// CFB_GEMM_TRACE=1: the 128-value clock trace buffer (cleared on the launch's stream), else null
+long long* gemm_trace_buffer(cudaStream_t st) {
+  if (!getenv("CFB_GEMM_TRACE")) return nullptr;
+  if (!g_gemm_trace) cudaMalloc(&g_gemm_trace, 128 * sizeof(long long));
+  cudaMemsetAsync(g_gemm_trace, 0, 128 * sizeof(long long), st);
+  return g_gemm_trace;
+}
 
 int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return 0;
@@ -439,14 +450,7 @@ int launch_gemm_tc(const GemmDesc& g, cudaStream_t st, std::string* err) {
   p.num_tiles = m_tiles * n_tiles;
   p.num_k_blocks = (g.K + kBlockK - 1) / kBlockK;
   p.dbg_nofence = getenv("CFB_GEMM_NOFENCE") != nullptr;
-  p.trace = nullptr;
-  if (getenv("CFB_GEMM_TRACE")) {
-    if (!g_gemm_trace) {
-      cudaMalloc(&g_gemm_trace, 128 * sizeof(long long));
-    }
-    cudaMemsetAsync(g_gemm_trace, 0, 128 * sizeof(long long), st);
-    p.trace = g_gemm_trace;
-  }
+  p.trace = gemm_trace_buffer(st);
   p.ep = g.ep;
   p.ep.M = g.M;
   p.ep.N = g.N;
