@@ -803,8 +803,9 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     ++launches;
   }
   // ---- subsampling: conv 1->C, conv C->C, linear (subsampling.py:172-175)
-  const char* c0_var = getenv("CFB_CONV0_GEMM");  // 0 = CUDA-core kernel; default: patch gather + tcgen05 GEMM
-  if (pk || (!v && !(c0_var != nullptr && atoi(c0_var) == 0))) {
+  // bf16 path: patch gather + tcgen05 GEMM (the same form dense and packed, so the two stay bit-identical); the CUDA-core
+  // kernel below serves the fp32 validation path
+  if (pk || !v) {
     if (pk) {
       CFB_TRY(launch_conv0_im2col_packed(feats, feats_dtype == CFB_BF16, reinterpret_cast<const long long*>(lengths),
                                          ws + pl.a0, pk->first, pk->step, h->F0, T, conv_out(T), h->F1, h->Fh, pk->n_rows, tb,
