@@ -45,6 +45,7 @@ constexpr int kKVBytes = 2 * kKBytes;
 constexpr int kBandSlots = 3;              // 64-row band blocks in flight (each is consumed by exactly one MMA)
 constexpr int kBlockBytes = 64 * kDK * 2;
 constexpr int kGSlots = 4;                 // TMEM ring of G blocks
+constexpr float kGScale = 16.f, kGScaleInv = 1.f / 16.f;  // (q + v) enters the fp16 G MMA divided by 16: headroom for its fp16 accumulator
 constexpr int kShiftPitch = 100;           // words per private shift row (96-column fp32 window + pad): 16-byte
                                            // stores and 4-byte loads at word offset (31 - lane) are conflict-free
 constexpr int kShiftBytes = 32 * kShiftPitch * 4;
@@ -95,7 +96,32 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   return v;
 }
 
-template <bool kInstr>  // kInstr: clock trace + ablation switches (timing experiments only)
+// 32 consecutive words from shared memory in one asm statement (see ptx::lds_f32x32)
+__device__ __forceinline__ void lds_u32x32(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "ld.shared.b32 %0, [%32+0];\n ld.shared.b32 %1, [%32+4];\n ld.shared.b32 %2, [%32+8];\n ld.shared.b32 %3, [%32+12];\n"
+      "ld.shared.b32 %4, [%32+16];\n ld.shared.b32 %5, [%32+20];\n ld.shared.b32 %6, [%32+24];\n ld.shared.b32 %7, [%32+28];\n"
+      "ld.shared.b32 %8, [%32+32];\n ld.shared.b32 %9, [%32+36];\n ld.shared.b32 %10, [%32+40];\n ld.shared.b32 %11, [%32+44];\n"
+      "ld.shared.b32 %12, [%32+48];\n ld.shared.b32 %13, [%32+52];\n ld.shared.b32 %14, [%32+56];\n ld.shared.b32 %15, [%32+60];\n"
+      "ld.shared.b32 %16, [%32+64];\n ld.shared.b32 %17, [%32+68];\n ld.shared.b32 %18, [%32+72];\n ld.shared.b32 %19, [%32+76];\n"
+      "ld.shared.b32 %20, [%32+80];\n ld.shared.b32 %21, [%32+84];\n ld.shared.b32 %22, [%32+88];\n ld.shared.b32 %23, [%32+92];\n"
+      "ld.shared.b32 %24, [%32+96];\n ld.shared.b32 %25, [%32+100];\n ld.shared.b32 %26, [%32+104];\n ld.shared.b32 %27, [%32+108];\n"
+      "ld.shared.b32 %28, [%32+112];\n ld.shared.b32 %29, [%32+116];\n ld.shared.b32 %30, [%32+120];\n ld.shared.b32 %31, [%32+124];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr)
+      : "memory");
+}
+// kind::f16 instruction descriptor with fp16 A / B and an fp16 accumulator (tools/ubench_f16acc.cu: bf16 operands with an
+// fp16 accumulator are an illegal instruction; an fp16 accumulator takes one 32-bit TMEM column per element)
+__host__ __device__ constexpr uint32_t make_idesc_f16_f16acc(int m, int n) {
+  return (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// kInstr: clock trace + ablation switches (timing experiments only)
+template <bool kInstr>
 __global__ void __launch_bounds__(kThreads, 1)
 rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmP,
                    const AttnParams p) {
@@ -296,8 +322,8 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       }
     } else {
       // ---------------------------------------------------------------------------------- G ring issuer
-      constexpr uint32_t idesc_g = ptx::make_idesc_bf16(kBM, 64, 0, 0);
-      constexpr uint32_t idesc_g3 = ptx::make_idesc_bf16(kBM, 192, 0, 0);
+      constexpr uint32_t idesc_g = make_idesc_f16_f16acc(kBM, 64);
+      constexpr uint32_t idesc_g3 = make_idesc_f16_f16acc(kBM, 192);
       const uint32_t tQv = tmem_base + kColQ + 32;
       const uint32_t band_base = sbase + kOffBand;
       ptx::mbar_wait_a(qv_ready, 0);
@@ -352,6 +378,13 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
     const uint32_t tP = t_lane + kColP + set * 32;
 
     // ---- this thread's row of Q+u (set 0) or Q+v (set 1) -> TMEM A operand
+    if (set == 1) {  // the G MMA takes fp16 operands: (q + v) / 16 as fp16 (exact for a bf16 value inside fp16's range)
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qw[c]));
+        qw[c] = pack_f16x2(f.x * kGScaleInv, f.y * kGScaleInv);
+      }
+    }
     ptx::tmem_st_x32(t_lane + kColQ + set * 32, qw);
     ptx::tc_wait_st();
     ptx::tc_fence_before();
@@ -363,34 +396,41 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
     // 64 kt + 96 - 32 quarter.  The window goes through a private fp32 shared-memory row: stored with 16-byte
     // stores while the P V MMA of the previous tile runs, read back at word offset 31 - lane when S arrives.
     const int sh = 31 - lane;
-    const uint32_t shift_row = sbase + kOffShift + (warp - 4) * kShiftBytes + lane * kShiftPitch * 4;
+    // 48 packed words per row, pitch 96 words plus a 16-byte skew ((lane / 2 + 4 (lane & 1)) mod 8) that keeps both the
+    // 16-byte stores and the 4-byte loads at word offset (31 - lane) / 2 conflict-free
+    const uint32_t shift_row = sbase + kOffShift + (warp - 4) * kShiftBytes + lane * 96 * 4 +
+                               static_cast<uint32_t>(((lane >> 1) + 4 * (lane & 1)) & 7) * 16;
     const int wcol = 96 - 32 * quarter;  // window start inside the concatenation of ring blocks kt, kt+1, kt+2
 
     auto fetch_window = [&](int kt, int tslot) {
       ptx::mbar_wait_a(g_full + 8 * ((kt + 2) % kGSlots), ((kt + 2) / kGSlots) & 1);  // blocks complete in order
       ptx::tc_fence_after();
       if (tslot) CFB_TR(tslot);
-      uint32_t w[96];
+      uint32_t w[49];
       if (dbg & 32) {
 #pragma unroll
-        for (int c = 0; c < 96; ++c) w[c] = 0u;
+        for (int c = 0; c < 48; ++c) w[c] = 0u;
       } else {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const int wc = wcol + 32 * c;
           const int blk = kt + (wc >> 6);
-          ptx::tmem_ld_x32(t_lane + kColG + (blk % kGSlots) * 64 + (wc & 63),
-                           *reinterpret_cast<uint32_t(*)[32]>(&w[32 * c]));
+          ptx::tmem_ld_x16_pack16(t_lane + kColG + (blk % kGSlots) * 64 + (wc & 63), &w[16 * c]);
         }
         ptx::tc_wait_ld();
       }
+      w[48] = 0u;
       if (tslot) CFB_TR(tslot + 1);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_a(g_free + 8 * set);
       if (!(dbg & 2)) {
+        // odd shifts: move the row down by one half so that the halves (31 - lane) + 2 j, + 2 j + 1 share a word
+        const uint32_t sel = (sh & 1) ? 0x5432u : 0x3210u;
 #pragma unroll
-        for (int q = 0; q < 24; ++q) ptx::sts128(shift_row + q * 16, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+        for (int m = 0; m < 48; ++m) w[m] = prmt(w[m], w[m + 1], sel);
+#pragma unroll
+        for (int q = 0; q < 12; ++q) ptx::sts128(shift_row + q * 16, w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
       }
     };
 
@@ -417,18 +457,25 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         ptx::tmem_ld_x32(tS + 32, s1r);
         ptx::tc_wait_ld();
         if (ts) CFB_TR(16 + it * 16 + 10);
-        float g[32];
+        uint32_t gw[32];
         if (dbg & 4) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) g[c] = 0.f;
+          for (int c = 0; c < 32; ++c) gw[c] = 0u;
         } else {
-          ptx::lds_f32x32(shift_row + sh * 4, g);
+          lds_u32x32(shift_row + (sh >> 1) * 4, gw);
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) sv[c] = __uint_as_float(s0r[c]) + g[c];
-        if (!(dbg & 4)) ptx::lds_f32x32(shift_row + sh * 4 + 128, g);
+        for (int c = 0; c < 16; ++c) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[c]));
+          sv[2 * c] = fmaf(f.x, kGScale, __uint_as_float(s0r[2 * c]));
+          sv[2 * c + 1] = fmaf(f.y, kGScale, __uint_as_float(s0r[2 * c + 1]));
+        }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) sv[32 + c] = __uint_as_float(s1r[c]) + g[c];
+        for (int c = 0; c < 16; ++c) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[16 + c]));
+          sv[32 + 2 * c] = fmaf(f.x, kGScale, __uint_as_float(s1r[2 * c]));
+          sv[32 + 2 * c + 1] = fmaf(f.y, kGScale, __uint_as_float(s1r[2 * c + 1]));
+        }
       }
       if (ts) CFB_TR(16 + it * 16 + 2);
       if (j0 + kBN > len) {  // only the last key tile can contain masked keys
@@ -553,6 +600,25 @@ long long* g_attn_trace = nullptr;
 
 }  // namespace
 
+// The G MMA reads fp16 positional projections.  cfb_forward converts its whole `pos` buffer once per call, in place
+// (launch_bf16_to_f16_inplace) and says so (pos_f16); the kernel-level entry point cfb_op_rel_attention takes bf16 like every
+// other operand and gets a copy here: a lazily grown scratch buffer -- that path allocates, the forward does not.
+const void* attn_pos_f16(const AttnDesc& a, int Dp, cudaStream_t st) {
+  if (a.pos_f16) return a.pos;
+  static void* scratch[64] = {};
+  static size_t elems[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t need = static_cast<size_t>(2 * a.T - 1) * Dp;
+  if (elems[dev & 63] < need) {
+    if (scratch[dev & 63]) cudaFree(scratch[dev & 63]);
+    cudaMalloc(&scratch[dev & 63], need * 2);
+    elems[dev & 63] = need;
+  }
+  launch_bf16_to_f16(a.pos, a.ld_pos, scratch[dev & 63], 2 * a.T - 1, Dp, st);
+  return scratch[dev & 63];
+}
+
 // debug: copies the clock trace of the last traced launch to the host (1024 values)
 extern "C" __attribute__((visibility("default"))) int cfb_debug_attn_trace(long long* host_out) {
   if (!g_attn_trace) return 1;
@@ -582,12 +648,13 @@ int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err) {
     uint32_t boxk[2] = {kDK, kBN};
     if (!encode_tmap_bf16(&tmKV, a.qkv, 2, dims, strides, boxk, err)) return -1;
   }
+  const void* pos16 = attn_pos_f16(a, Dp, st);  // fp16 copy of the projections the G MMA reads (in place in the engine's forward)
   {
-    // a.pos points at this layer's first column inside the (2T-1, ld_pos) positional projection buffer
+    // 2-byte elements: the number format is the MMA's business, not the tensor map's
     uint64_t dims[2] = {static_cast<uint64_t>(Dp), static_cast<uint64_t>(2 * a.T - 1)};
-    uint64_t strides[1] = {static_cast<uint64_t>(a.ld_pos) * 2};
+    uint64_t strides[1] = {static_cast<uint64_t>(a.pos_f16 ? a.ld_pos : Dp) * 2};
     uint32_t box[2] = {kDK, 64};
-    if (!encode_tmap_bf16(&tmP, a.pos, 2, dims, strides, box, err)) return -1;
+    if (!encode_tmap_bf16(&tmP, pos16, 2, dims, strides, box, err)) return -1;
   }
   static bool configured[64] = {};
   int dev = 0;

@@ -53,6 +53,7 @@ constexpr int kKVBytes = 2 * kKBytes;
 constexpr int kBandSlots = 3;              // 64-row band blocks in flight (each is consumed by exactly one MMA)
 constexpr int kBlockBytes = 64 * kDK * 2;
 constexpr int kGSlots = 4;                 // TMEM ring of G blocks
+constexpr float kGScale = 16.f, kGScaleInv = 1.f / 16.f;  // (q + v) enters the fp16 G MMA divided by 16 (attention_tc.cu)
 constexpr int kShiftPitch = 100;           // words per private shift row (96-column fp32 window + pad): 16-byte
                                            // stores and 4-byte loads at word offset (31 - lane) are conflict-free
 constexpr int kShiftBytes = 32 * kShiftPitch * 4;
@@ -103,6 +104,30 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   return v;
 }
 
+
+// 32 consecutive words from shared memory in one asm statement (see ptx::lds_f32x32)
+__device__ __forceinline__ void lds_u32x32(uint32_t addr, uint32_t (&v)[32]) {
+  asm volatile(
+      "ld.shared.b32 %0, [%32+0];\n ld.shared.b32 %1, [%32+4];\n ld.shared.b32 %2, [%32+8];\n ld.shared.b32 %3, [%32+12];\n"
+      "ld.shared.b32 %4, [%32+16];\n ld.shared.b32 %5, [%32+20];\n ld.shared.b32 %6, [%32+24];\n ld.shared.b32 %7, [%32+28];\n"
+      "ld.shared.b32 %8, [%32+32];\n ld.shared.b32 %9, [%32+36];\n ld.shared.b32 %10, [%32+40];\n ld.shared.b32 %11, [%32+44];\n"
+      "ld.shared.b32 %12, [%32+48];\n ld.shared.b32 %13, [%32+52];\n ld.shared.b32 %14, [%32+56];\n ld.shared.b32 %15, [%32+60];\n"
+      "ld.shared.b32 %16, [%32+64];\n ld.shared.b32 %17, [%32+68];\n ld.shared.b32 %18, [%32+72];\n ld.shared.b32 %19, [%32+76];\n"
+      "ld.shared.b32 %20, [%32+80];\n ld.shared.b32 %21, [%32+84];\n ld.shared.b32 %22, [%32+88];\n ld.shared.b32 %23, [%32+92];\n"
+      "ld.shared.b32 %24, [%32+96];\n ld.shared.b32 %25, [%32+100];\n ld.shared.b32 %26, [%32+104];\n ld.shared.b32 %27, [%32+108];\n"
+      "ld.shared.b32 %28, [%32+112];\n ld.shared.b32 %29, [%32+116];\n ld.shared.b32 %30, [%32+120];\n ld.shared.b32 %31, [%32+124];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr)
+      : "memory");
+}
+// kind::f16 instruction descriptor with fp16 A / B and an fp16 accumulator (tools/ubench_f16acc.cu: bf16 operands with an
+// fp16 accumulator are an illegal instruction; an fp16 accumulator takes one 32-bit TMEM column per element)
+__host__ __device__ constexpr uint32_t make_idesc_f16_f16acc(int m, int n) {
+  return (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmP,
@@ -297,7 +322,7 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       }
     } else {
       // ---------------------------------------------------------------------------------- G ring issuer
-      constexpr uint32_t idesc_g = ptx::make_idesc_bf16(kBM, 64, 0, 0);
+      constexpr uint32_t idesc_g = make_idesc_f16_f16acc(kBM, 64);
       const uint32_t tQv = tmem_base + kColQ + 32;
       const uint32_t band_base = sbase + kOffBand;
       int base_gb = 0, n_act = 0;
@@ -353,7 +378,9 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     const uint32_t tS = t_lane + kColS + set * 64;
     const uint32_t tP = t_lane + kColP + set * 32;
     const int sh = 31 - lane;
-    const uint32_t shift_row = sbase + kOffShift + (warp - 4) * kShiftBytes + lane * kShiftPitch * 4;
+    // 48 packed fp16 pairs per row, pitch 96 words plus a 16-byte skew: conflict-free 16-byte stores and 4-byte loads (attention_tc.cu)
+    const uint32_t shift_row = sbase + kOffShift + (warp - 4) * kShiftBytes + lane * 96 * 4 +
+                               static_cast<uint32_t>(((lane >> 1) + 4 * (lane & 1)) & 7) * 16;
     const int wcol = 96 - 32 * quarter;  // window start inside the concatenation of ring blocks kt, kt+1, kt+2
     const uint32_t xrow = sbase + kOffX + ii * kXPitch * 4;
     const float scale = p.scale_log2;
@@ -388,6 +415,13 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     // signal item n before all three issuer warps have passed their operand wait of item n - 1 (an issuer with no tile
     // in an item could otherwise be lapped).
     auto store_q = [&](int n_started) {
+      if (set == 1) {  // the G MMA takes fp16 operands: (q + v) / 16 as fp16
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qw[c]));
+          qw[c] = pack_f16x2(f.x * kGScaleInv, f.y * kGScaleInv);
+        }
+      }
       ptx::tmem_st_x32(t_lane + kColQ + set * 32, qw);
       ptx::tc_wait_st();
       ptx::tc_fence_before();
@@ -417,19 +451,24 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         const int last = base_gb + kt + 2;  // blocks complete in order
         ptx::mbar_wait_a(g_full + 8 * (last % kGSlots), (last / kGSlots) & 1);
         ptx::tc_fence_after();
-        uint32_t wv[96];
+        uint32_t wv[49];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const int wc = wcol + 32 * c;
           const int blk = base_gb + kt + (wc >> 6);
-          ptx::tmem_ld_x32(t_lane + kColG + (blk % kGSlots) * 64 + (wc & 63), *reinterpret_cast<uint32_t(*)[32]>(&wv[32 * c]));
+          ptx::tmem_ld_x16_pack16(t_lane + kColG + (blk % kGSlots) * 64 + (wc & 63), &wv[16 * c]);
         }
         ptx::tc_wait_ld();
+        wv[48] = 0u;
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_a(g_free + 8 * set);
+        // odd shifts: move the row down by one half so that the halves (31 - lane) + 2 j, + 2 j + 1 share a word
+        const uint32_t sel = (sh & 1) ? 0x5432u : 0x3210u;
 #pragma unroll
-        for (int q = 0; q < 24; ++q) ptx::sts128(shift_row + q * 16, wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
+        for (int m = 0; m < 48; ++m) wv[m] = prmt(wv[m], wv[m + 1], sel);
+#pragma unroll
+        for (int q = 0; q < 12; ++q) ptx::sts128(shift_row + q * 16, wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
       };
 
       float o_acc[kDK];
@@ -450,13 +489,20 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           ptx::tmem_ld_x32(tS, s0r);
           ptx::tmem_ld_x32(tS + 32, s1r);
           ptx::tc_wait_ld();
-          float g[32];
-          ptx::lds_f32x32(shift_row + sh * 4, g);
+          uint32_t gw[32];
+          lds_u32x32(shift_row + (sh >> 1) * 4, gw);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) sv[c] = __uint_as_float(s0r[c]) + g[c];
-          ptx::lds_f32x32(shift_row + sh * 4 + 128, g);
+          for (int c = 0; c < 16; ++c) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[c]));
+            sv[2 * c] = fmaf(f.x, kGScale, __uint_as_float(s0r[2 * c]));
+            sv[2 * c + 1] = fmaf(f.y, kGScale, __uint_as_float(s0r[2 * c + 1]));
+          }
 #pragma unroll
-          for (int c = 0; c < 32; ++c) sv[32 + c] = __uint_as_float(s1r[c]) + g[c];
+          for (int c = 0; c < 16; ++c) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[16 + c]));
+            sv[32 + 2 * c] = fmaf(f.x, kGScale, __uint_as_float(s1r[2 * c]));
+            sv[32 + 2 * c + 1] = fmaf(f.y, kGScale, __uint_as_float(s1r[2 * c + 1]));
+          }
         }
         if (j0 + kBN > len) {  // only the last key tile can contain masked keys
 #pragma unroll
@@ -585,10 +631,12 @@ int launch_attn_tcp(const AttnDesc& a, cudaStream_t st, std::string* err) {
     if (!encode_tmap_bf16(&tmKV, a.qkv, 2, dims, strides, boxk, err)) return -1;
   }
   {
+    // fp16 copy of the projections the G MMA reads (converted in place once per forward by the engine; see attention_tc.cu)
+    const void* pos16 = attn_pos_f16(a, Dp, st);
     uint64_t dims[2] = {static_cast<uint64_t>(Dp), static_cast<uint64_t>(2 * a.T - 1)};
-    uint64_t strides[1] = {static_cast<uint64_t>(a.ld_pos) * 2};
+    uint64_t strides[1] = {static_cast<uint64_t>(a.pos_f16 ? a.ld_pos : Dp) * 2};
     uint32_t box[2] = {kDK, 64};
-    if (!encode_tmap_bf16(&tmP, a.pos, 2, dims, strides, box, err)) return -1;
+    if (!encode_tmap_bf16(&tmP, pos16, 2, dims, strides, box, err)) return -1;
   }
   static bool configured[64] = {};
   static int sms[64] = {};

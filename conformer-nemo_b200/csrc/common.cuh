@@ -63,6 +63,7 @@ struct AttnDesc {
   int B = 0, T = 0, H = 0, dk = 0, dkp = 0;
   // packed batches (PackedTables): qkv / ctx have `rows` token rows, every sequence owns a slot of them; T stays the
   // extent of the positional table (the longest sequence).  tiles == nullptr: the dense (B, T) layout above.
+  bool pos_f16 = false;  // pos already holds fp16 (the engine converts its buffer once per forward); false: bf16
   const int4* tiles = nullptr;  // [n_tiles] (sequence, first query row i0, first token row of the slot, rows in the slot)
   int n_tiles = 0;
   long long rows = 0;
@@ -140,6 +141,10 @@ int launch_attn_tc(const AttnDesc& a, cudaStream_t st, std::string* err);
 // persistent form (one CTA per SM walks over the (query tile, head, sequence) items; attention_tcp.cu)
 int launch_attn_tcp(const AttnDesc& a, cudaStream_t st, std::string* err);
 int launch_attn_simt(const AttnDesc& a, cudaStream_t st, std::string* err);
+// fp16 view of the positional projections for the tensor-core attention kernels (attention_tc.cu)
+const void* attn_pos_f16(const AttnDesc& a, int Dp, cudaStream_t st);
+// bf16 (rows x cols, leading dimension ld) -> fp16 (rows x cols, dense); dst == src with ld == cols converts in place
+int launch_bf16_to_f16(const void* src, long long ld, void* dst, long long rows, int cols, cudaStream_t st);
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int rows, int d,
                      const int32_t* lens, int frames_per_seq, cudaStream_t st);

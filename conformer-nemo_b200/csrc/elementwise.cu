@@ -2,6 +2,8 @@
 // the first 1->C strided convolution of the subsampling stack, the relative positional table, calc_length, and the
 // validation path's im2col.  All are coalesced along the channel dimension with 128-bit accesses; reductions use
 // warp shuffles; the depth-wise kernel stages its time halo in shared memory.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace cfb {
@@ -528,7 +530,38 @@ __global__ void im2col_kernel(const float* __restrict__ y, float* __restrict__ c
   }
 }
 
+// ------------------------------------------------------------------------------------------------ bf16 -> fp16
+// eight elements per thread (cols % 8 == 0); element-wise, so dst may alias src when both are dense
+__global__ void __launch_bounds__(256) bf16_to_f16_kernel(const bf16* src, long long ld, __half* dst, long long rows, int cols) {
+  const int c8 = cols >> 3;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (i >= rows * c8) return;
+  const long long r = i / c8;
+  const int c = static_cast<int>(i - r * c8) * 8;
+  const uint4 u = *reinterpret_cast<const uint4*>(src + r * ld + c);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+    const __half2 hh = __floats2half2_rn(f.x, f.y);
+    o[k] = *reinterpret_cast<const uint32_t*>(&hh);
+  }
+  *reinterpret_cast<uint4*>(dst + r * cols + c) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 }  // namespace
+int launch_bf16_to_f16(const void* src, long long ld, void* dst, long long rows, int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (cols % 8 != 0 || ld % 8 != 0) return -1;
+  const long long n = rows * (cols >> 3);
+  launch_pdl(bf16_to_f16_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st,
+             reinterpret_cast<const bf16*>(src), ld, reinterpret_cast<__half*>(dst), rows, cols);
+  return static_cast<int>(cudaGetLastError());
+}
+
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, bool out_bf16, int rows, int d,
                      const int32_t* lens, int frames_per_seq, cudaStream_t st) {

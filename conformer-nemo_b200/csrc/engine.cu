@@ -875,6 +875,12 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
     ep.ldo = static_cast<long long>(L) * Dp;
     CFB_TRY(gemm(ws + pl.pe, d, h->w_pos, d, pl.P, L * Dp, d, EPI_LINEAR, abf, ep, "linear_pos"), "linear_pos");
   }
+  if (abf) {
+    // the attention kernels compute the position term from fp16 operands into an fp16 accumulator (attention_tc.cu): the
+    // projections of all layers are converted once, in place
+    CFB_TRY(launch_bf16_to_f16(ws + pl.pos, static_cast<long long>(L) * Dp, ws + pl.pos, pl.P, L * Dp, st), "linear_pos -> fp16");
+    ++launches;
+  }
 
   const int32_t* lens = encoded_len;
   void* a = ws + pl.a;
@@ -898,6 +904,7 @@ static int forward_range(cfb_handle* h, const void* feats, int feats_dtype, cons
         ad.qkv = ws + pl.qkv;
         ad.pos = ws + pl.pos + static_cast<size_t>(l) * Dp * h->esz();
         ad.ld_pos = static_cast<long long>(L) * Dp;
+        ad.pos_f16 = abf;
         ad.ctx = ws + pl.ctx;
         ad.lens = lens;
         ad.B = B;
