@@ -447,6 +447,14 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       const int j0 = kt * kBN;
       const bool ts = kInstr && warp == 4 && it < 30;
       if (ts) CFB_TR(16 + it * 16 + 0);
+      // the shifted window row was stored a whole P V MMA ago: read it while the S MMA of this tile is still in flight
+      uint32_t gw[32];
+      if (dbg & 4) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) gw[c] = 0u;
+      } else {
+        lds_u32x32(shift_row + (sh >> 1) * 4, gw);
+      }
       ptx::mbar_wait_a(sg_full + 8 * set, it & 1);
       ptx::tc_fence_after();
       if (ts) CFB_TR(16 + it * 16 + 1);
@@ -457,13 +465,6 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         ptx::tmem_ld_x32(tS + 32, s1r);
         ptx::tc_wait_ld();
         if (ts) CFB_TR(16 + it * 16 + 10);
-        uint32_t gw[32];
-        if (dbg & 4) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) gw[c] = 0u;
-        } else {
-          lds_u32x32(shift_row + (sh >> 1) * 4, gw);
-        }
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[c]));

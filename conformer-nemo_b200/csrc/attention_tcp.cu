@@ -481,6 +481,9 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       for (int kt = set; kt < n_kt; kt += 2, ++it) {
         const int j0 = kt * kBN;
         const int gi = base_it[set] + it;
+        // the shifted window row was stored a whole P V MMA ago: read it while the S MMA of this tile is still in flight
+        uint32_t gw[32];
+        lds_u32x32(shift_row + (sh >> 1) * 4, gw);
         ptx::mbar_wait_a(sg_full + 8 * set, gi & 1);
         ptx::tc_fence_after();
         float sv[kBN];
@@ -489,8 +492,6 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           ptx::tmem_ld_x32(tS, s0r);
           ptx::tmem_ld_x32(tS + 32, s1r);
           ptx::tc_wait_ld();
-          uint32_t gw[32];
-          lds_u32x32(shift_row + (sh >> 1) * 4, gw);
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[c]));
