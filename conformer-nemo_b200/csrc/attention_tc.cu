@@ -455,6 +455,12 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       } else {
         lds_u32x32(shift_row + (sh >> 1) * 4, gw);
       }
+      float gf[kBN];  // 16 g is exact, so 16 g + s below equals the fused form bit for bit
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[c]));
+        gf[2 * c] = f.x * kGScale, gf[2 * c + 1] = f.y * kGScale;
+      }
       ptx::mbar_wait_a(sg_full + 8 * set, it & 1);
       ptx::tc_fence_after();
       if (ts) CFB_TR(16 + it * 16 + 1);
@@ -466,16 +472,9 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         ptx::tc_wait_ld();
         if (ts) CFB_TR(16 + it * 16 + 10);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[c]));
-          sv[2 * c] = fmaf(f.x, kGScale, __uint_as_float(s0r[2 * c]));
-          sv[2 * c + 1] = fmaf(f.y, kGScale, __uint_as_float(s0r[2 * c + 1]));
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[16 + c]));
-          sv[32 + 2 * c] = fmaf(f.x, kGScale, __uint_as_float(s1r[2 * c]));
-          sv[32 + 2 * c + 1] = fmaf(f.y, kGScale, __uint_as_float(s1r[2 * c + 1]));
+        for (int c = 0; c < 32; ++c) {
+          sv[c] = gf[c] + __uint_as_float(s0r[c]);
+          sv[32 + c] = gf[32 + c] + __uint_as_float(s1r[c]);
         }
       }
       if (ts) CFB_TR(16 + it * 16 + 2);

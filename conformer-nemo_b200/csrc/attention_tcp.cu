@@ -511,7 +511,9 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
             if (j0 + c >= len) sv[c] = -INFINITY;
         }
         // the exponentials of consecutive key tiles take turns on the MUFU pipe (tile kt after tile kt-1)
-        if (kt > 0) ptx::mbar_wait_a(exp_done + 8 * (set ^ 1), (base_it[set ^ 1] + (set == 0 ? it - 1 : it)) & 1);
+        // (with one tile per set the order does not matter and set 1 need not idle through set 0's write-back of the
+        // previous item: 128 x 100 frames x 4 heads 30.8 -> 29.5 us; with more tiles the strict order measures better)
+        if (kt > (n_kt <= 2 ? 1 : 0)) ptx::mbar_wait_a(exp_done + 8 * (set ^ 1), (base_it[set ^ 1] + (set == 0 ? it - 1 : it)) & 1);
         float mx4[4] = {sv[0], sv[1], sv[2], sv[3]};
 #pragma unroll
         for (int c = 4; c < kBN; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], sv[c]);
