@@ -45,6 +45,7 @@ constexpr int kKVBytes = 2 * kKBytes;
 constexpr int kBandSlots = 3;              // 64-row band blocks in flight (each is consumed by exactly one MMA)
 constexpr int kBlockBytes = 64 * kDK * 2;
 constexpr int kGSlots = 4;                 // TMEM ring of G blocks
+constexpr uint16_t kGScaleH = 0x4C00;  // kGScale as fp16
 constexpr float kGScale = 16.f, kGScaleInv = 1.f / 16.f;  // (q + v) enters the fp16 G MMA divided by 16: headroom for its fp16 accumulator
 constexpr int kShiftPitch = 100;           // words per private shift row (96-column fp32 window + pad): 16-byte
                                            // stores and 4-byte loads at word offset (31 - lane) are conflict-free
@@ -455,12 +456,6 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       } else {
         lds_u32x32(shift_row + (sh >> 1) * 4, gw);
       }
-      float gf[kBN];  // 16 g is exact, so 16 g + s below equals the fused form bit for bit
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[c]));
-        gf[2 * c] = f.x * kGScale, gf[2 * c + 1] = f.y * kGScale;
-      }
       ptx::mbar_wait_a(sg_full + 8 * set, it & 1);
       ptx::tc_fence_after();
       if (ts) CFB_TR(16 + it * 16 + 1);
@@ -472,9 +467,10 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
         ptx::tc_wait_ld();
         if (ts) CFB_TR(16 + it * 16 + 10);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          sv[c] = gf[c] + __uint_as_float(s0r[c]);
-          sv[32 + c] = gf[32 + c] + __uint_as_float(s1r[c]);
+        for (int c = 0; c < 16; ++c) {  // s + 16 g, g an fp16 half of the packed window word (FHFMA: no conversion)
+          ptx::fhfma_pair(gw[c], kGScaleH, __uint_as_float(s0r[2 * c]), __uint_as_float(s0r[2 * c + 1]), sv[2 * c], sv[2 * c + 1]);
+          ptx::fhfma_pair(gw[16 + c], kGScaleH, __uint_as_float(s1r[2 * c]), __uint_as_float(s1r[2 * c + 1]), sv[32 + 2 * c],
+                          sv[32 + 2 * c + 1]);
         }
       }
       if (ts) CFB_TR(16 + it * 16 + 2);
@@ -495,22 +491,25 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
       const float m_new = fmaxf(m_run, mx);  // finite: every tile holds at least one key j < len
       const float ms = m_new * scale;
       const float alpha = fast_exp2(fmaf(m_run, scale, -ms));
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      // two fp32 lanes per instruction where the math allows (FFMA2 / FADD2, ptx.cuh): these warps are bound by the
+      // length of their instruction stream
+      float2 rs4[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+      const float2 scale2 = make_float2(scale, scale), nms2 = make_float2(-ms, -ms), alpha2 = make_float2(alpha, alpha);
       uint32_t pw[32];
 #pragma unroll
       for (int m = 0; m < 32; ++m) {
-        const float a0 = fmaf(sv[2 * m], scale, -ms), a1 = fmaf(sv[2 * m + 1], scale, -ms);
-        const float e0 = (dbg & 1) ? a0 : fast_exp2(a0);
-        const float e1 = (dbg & 1) ? a1 : fast_exp2(a1);
-        rs4[m & 3] += e0 + e1;
+        const float2 a = ptx::ffma2(make_float2(sv[2 * m], sv[2 * m + 1]), scale2, nms2);
+        const float2 e = make_float2((dbg & 1) ? a.x : fast_exp2(a.x), (dbg & 1) ? a.y : fast_exp2(a.y));
+        rs4[m & 3] = ptx::fadd2(rs4[m & 3], e);
         // bf16 pair without the conversion unit (it shares the MUFU pipe): round half up with integer adds, one PRMT
-        pw[m] = prmt(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632u);
+        pw[m] = prmt(__float_as_uint(e.x) + 0x8000u, __float_as_uint(e.y) + 0x8000u, 0x7632u);
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_a(exp_done + 8 * set);
       if (ts) CFB_TR(16 + it * 16 + 3);
       ptx::tmem_st_x32(tP, pw);
-      const float rsum = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      const float2 rs2 = ptx::fadd2(ptx::fadd2(rs4[0], rs4[1]), ptx::fadd2(rs4[2], rs4[3]));
+      const float rsum = rs2.x + rs2.y;
       l_run = fmaf(l_run, alpha, rsum);
       m_run = m_new;
       ptx::tc_wait_st();
@@ -536,9 +535,12 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
           ptx::tc_wait_ld();
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          o_acc[c] = fmaf(o_acc[c], alpha, __uint_as_float(a0[c]));
-          o_acc[32 + c] = fmaf(o_acc[32 + c], alpha, __uint_as_float(a1[c]));
+        for (int c = 0; c < 16; ++c) {
+          const float2 x = ptx::ffma2(make_float2(o_acc[2 * c], o_acc[2 * c + 1]), alpha2,
+                                      make_float2(__uint_as_float(a0[2 * c]), __uint_as_float(a0[2 * c + 1])));
+          const float2 y = ptx::ffma2(make_float2(o_acc[32 + 2 * c], o_acc[33 + 2 * c]), alpha2,
+                                      make_float2(__uint_as_float(a1[2 * c]), __uint_as_float(a1[2 * c + 1])));
+          o_acc[2 * c] = x.x, o_acc[2 * c + 1] = x.y, o_acc[32 + 2 * c] = y.x, o_acc[33 + 2 * c] = y.y;
         }
       }
       ptx::tc_fence_before();

@@ -54,6 +54,7 @@ constexpr int kBandSlots = 3;              // 64-row band blocks in flight (each
 constexpr int kBlockBytes = 64 * kDK * 2;
 constexpr int kGSlots = 4;                 // TMEM ring of G blocks
 constexpr float kGScale = 16.f, kGScaleInv = 1.f / 16.f;  // (q + v) enters the fp16 G MMA divided by 16 (attention_tc.cu)
+constexpr uint16_t kGScaleH = 0x4C00;                     // kGScale as fp16
 constexpr int kShiftPitch = 100;           // words per private shift row (96-column fp32 window + pad): 16-byte
                                            // stores and 4-byte loads at word offset (31 - lane) are conflict-free
 constexpr int kShiftBytes = 32 * kShiftPitch * 4;
@@ -493,16 +494,10 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           ptx::tmem_ld_x32(tS + 32, s1r);
           ptx::tc_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[c]));
-            sv[2 * c] = fmaf(f.x, kGScale, __uint_as_float(s0r[2 * c]));
-            sv[2 * c + 1] = fmaf(f.y, kGScale, __uint_as_float(s0r[2 * c + 1]));
-          }
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&gw[16 + c]));
-            sv[32 + 2 * c] = fmaf(f.x, kGScale, __uint_as_float(s1r[2 * c]));
-            sv[32 + 2 * c + 1] = fmaf(f.y, kGScale, __uint_as_float(s1r[2 * c + 1]));
+          for (int c = 0; c < 16; ++c) {  // s + 16 g, g an fp16 half of the packed window word
+            ptx::fhfma_pair(gw[c], kGScaleH, __uint_as_float(s0r[2 * c]), __uint_as_float(s0r[2 * c + 1]), sv[2 * c], sv[2 * c + 1]);
+            ptx::fhfma_pair(gw[16 + c], kGScaleH, __uint_as_float(s1r[2 * c]), __uint_as_float(s1r[2 * c + 1]), sv[32 + 2 * c],
+                            sv[32 + 2 * c + 1]);
           }
         }
         if (j0 + kBN > len) {  // only the last key tile can contain masked keys
@@ -521,18 +516,18 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         const float m_new = fmaxf(m_run, mx);  // finite: every tile holds at least one key j < len
         const float ms = m_new * scale;
         const float alpha = fast_exp2(fmaf(m_run, scale, -ms));
-        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 rs4[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
         uint32_t pw[32];
 #pragma unroll
-        for (int m = 0; m < 32; ++m) {
-          const float e0 = fast_exp2(fmaf(sv[2 * m], scale, -ms)), e1 = fast_exp2(fmaf(sv[2 * m + 1], scale, -ms));
-          rs4[m & 3] += e0 + e1;
-          pw[m] = prmt(__float_as_uint(e0) + 0x8000u, __float_as_uint(e1) + 0x8000u, 0x7632u);
+        for (int m = 0; m < 32; ++m) {  // scalar here (the packed forms of attention_tc.cu measure slower in this kernel), same order
+          const float2 e = make_float2(fast_exp2(fmaf(sv[2 * m], scale, -ms)), fast_exp2(fmaf(sv[2 * m + 1], scale, -ms)));
+          rs4[m & 3].x += e.x, rs4[m & 3].y += e.y;
+          pw[m] = prmt(__float_as_uint(e.x) + 0x8000u, __float_as_uint(e.y) + 0x8000u, 0x7632u);
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_a(exp_done + 8 * set);
         ptx::tmem_st_x32(tP, pw);
-        const float rsum = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+        const float rsum = ((rs4[0].x + rs4[1].x) + (rs4[2].x + rs4[3].x)) + ((rs4[0].y + rs4[1].y) + (rs4[2].y + rs4[3].y));
         l_run = fmaf(l_run, alpha, rsum);
         m_run = m_new;
         ptx::tc_wait_st();

@@ -270,6 +270,35 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 
+// Two fp32 lanes per instruction (FFMA2 / FADD2): same IEEE results per lane, half the issue slots.  For warps that are
+// bound by the length of their own instruction stream, not by the FMA pipe (the pipe still takes two cycles).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+// d = float(h) * float(m) + c with the fp16 operands read straight from the halves of a packed register (FHFMA: no
+// separate conversion); one rounding, so equal to fmaf(__half2float(h), __half2float(m), c)
+__device__ __forceinline__ void fhfma_pair(uint32_t h2, uint16_t m, float c0, float c1, float& d0, float& d1) {
+  asm("{.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tfma.rn.f32.f16 %0, lo, %3, %4;\n\tfma.rn.f32.f16 %1, hi, %3, %5;}"
+      : "=f"(d0), "=f"(d1)
+      : "r"(h2), "h"(m), "f"(c0), "f"(c1));
+}
+
 // explicit shared-space accesses (the compiler falls back to generic LD/ST when it cannot prove the address space)
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
