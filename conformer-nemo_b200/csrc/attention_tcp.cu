@@ -140,7 +140,10 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
   const int lane = tid & 31;
 
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  // Laundered through a volatile mov: ptxas otherwise REMATERIALISES the base wherever it is short of registers, and the
+  // recipe starts with S2R SR_CgaCtaId (tens of cycles) -- twice per key tile in the softmax warps (ncu source page).
+  uint32_t sbase;
+  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((ptx::smem_u32(smem_raw) + 1023u) & ~1023u));
   const uint32_t bar0 = sbase + kOffBar;
   const uint32_t qu_ready = bar0 + 0;    // Q+u of the current item is in TMEM (4 warp arrivals, softmax set 0)
   const uint32_t qv_ready = bar0 + 8;    // Q+v (softmax set 1)
