@@ -65,7 +65,9 @@ constexpr int kOffShift = kOffBand + kBandSlots * kBlockBytes;
 constexpr int kOffBar = kOffShift + 8 * kShiftBytes;
 constexpr int kBarBytes = 512;
 constexpr int kOffX = kOffBar + kBarBytes;  // set exchange (m, l, O[64]) x 128 rows: its own buffer (the K/V ring is busy)
-constexpr int kSmemTotal = kOffX + 4 * 32 * kXPitch * 4 + 1024;
+constexpr int kItemCap = 64;                // work items of this CTA decoded once into shared memory (32 B each)
+constexpr int kOffItems = kOffX + 4 * 32 * kXPitch * 4;
+constexpr int kSmemTotal = kOffItems + kItemCap * 32 + 1024;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColQ = 0, kColS = 64, kColP = 192, kColG = 256;
 
@@ -195,21 +197,18 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  pdl_launch_dependents();
-  pdl_wait();
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-
   // item -> (query tile, head, sequence) and the tile counts every role derives identically
   struct Item {
     int i0, h, b, len, n_kt, n_gb;
     int rb, S;  // first token row and row count of the sequence (dense: b T and T; packed: its slot)
     bool active;
   };
-  auto decode = [&](int item) {
+  auto finish = [](Item& it) {
+    it.active = it.i0 < it.len;  // otherwise the whole query tile is padding: the context rows are zero
+    it.n_kt = it.active ? (it.len + kBN - 1) / kBN : 0;
+    it.n_gb = it.active ? it.n_kt + 2 : 0;
+  };
+  auto decode_direct = [&](int item) {
     Item it;
     const int qt = item % p.n_qt;
     const int r = item / p.n_qt;
@@ -225,15 +224,49 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       it.S = T;
     }
     it.len = min(__ldg(p.lens + it.b), it.S);
-    it.active = it.i0 < it.len;  // otherwise the whole query tile is padding: the context rows are zero
-    it.n_kt = it.active ? (it.len + kBN - 1) / kBN : 0;
-    it.n_gb = it.active ? it.n_kt + 2 : 0;
+    finish(it);
     return it;
   };
   const int item0 = blockIdx.x, item_step = gridDim.x;
-  auto has_next_active = [&](int item) {
+  const int n_mine = item0 < p.n_items ? (p.n_items - item0 + item_step - 1) / item_step : 0;
+  const uint32_t item_tab = sbase + kOffItems;
+
+  pdl_launch_dependents();
+  pdl_wait();
+  // Every role walks the same item list; the divisions and the dependent length load of a decode sat on the softmax
+  // warps' path between items (ncu source page: long-scoreboard stalls in the merge / write-back part).  The first
+  // kItemCap items are decoded here once, in parallel, with the "is any later item active" answer the exchange barrier needs.
+  for (int k = tid; k < min(n_mine, kItemCap); k += kThreads) {
+    const Item it = decode_direct(item0 + k * item_step);
+    int later = 0;
+    for (int j = k + 1; j < n_mine && !later; ++j) later = decode_direct(item0 + j * item_step).active ? 1 : 0;
+    ptx::sts128(item_tab + 32 * k, it.i0, it.h, it.b, it.len);
+    ptx::sts128(item_tab + 32 * k + 16, it.rb, it.S, later, 0);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  // k = position in this CTA's list; every loop below carries it along (no division by the grid size per decode)
+  auto decode = [&](int item, int k) {
+    if (k >= kItemCap) return decode_direct(item);
+    Item it;
+    const float4 a = lds_f32x4(item_tab + 32 * k), c = lds_f32x4(item_tab + 32 * k + 16);
+    it.i0 = __float_as_int(a.x), it.h = __float_as_int(a.y), it.b = __float_as_int(a.z), it.len = __float_as_int(a.w);
+    it.rb = __float_as_int(c.x), it.S = __float_as_int(c.y);
+    finish(it);
+    return it;
+  };
+  auto has_next_active = [&](int item, int k) {
+    if (k < kItemCap) {
+      uint32_t later;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(later) : "r"(item_tab + 32 * k + 24) : "memory");
+      return later != 0;
+    }
     for (int j = item + item_step; j < p.n_items; j += item_step)
-      if (decode(j).active) return true;
+      if (decode_direct(j).active) return true;
     return false;
   };
 
@@ -243,8 +276,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       // ---------------------------------------------------------------------------------- TMA producer
       if (lane == 0) {
         int base_kv = 0, base_gb = 0;  // K/V tiles and band blocks loaded so far: ring positions stay continuous
-        for (int item = item0; item < p.n_items; item += item_step) {
-          const Item w = decode(item);
+        for (int item = item0, ik = 0; item < p.n_items; item += item_step, ++ik) {
+          const Item w = decode(item, ik);
           if (!w.active) continue;
           const int r0 = T - 1 - w.i0 - (kBM - 1);  // band row of G column 0 of block 0 (may be < 0: TMA zero-fills)
           auto load_band_block = [&](int g) {
@@ -286,8 +319,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       const uint32_t tS = tmem_base + kColS + s * 64;
       const uint32_t tP = tmem_base + kColP + s * 32;
       int base_kv = 0, base_it = 0, n_act = 0;
-      for (int item = item0; item < p.n_items; item += item_step) {
-        const Item w = decode(item);
+      for (int item = item0, ik = 0; item < p.n_items; item += item_step, ++ik) {
+        const Item w = decode(item, ik);
         if (!w.active) continue;
         ptx::mbar_wait_a(qu_ready, n_act & 1);
         ptx::tc_fence_after();
@@ -332,8 +365,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       int base_gb = 0, n_act = 0;
       int base_it[2] = {0, 0};
       int prev_its[2] = {0, 0};
-      for (int item = item0; item < p.n_items; item += item_step) {
-        const Item w = decode(item);
+      for (int item = item0, ik = 0; item < p.n_items; item += item_step, ++ik) {
+        const Item w = decode(item, ik);
         if (!w.active) continue;
         ptx::mbar_wait_a(qv_ready, n_act & 1);
         if (lane == 0) ptx::mbar_arrive_a(role_sync);
@@ -391,8 +424,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
 
     // this thread's row of Q+u (set 0) / Q+v (set 1) of an item: 64 bf16
     uint32_t qw[32];
-    auto fetch_q = [&](int item) {
-      const Item f = decode(item);
+    auto fetch_q = [&](int item, int k) {
+      const Item f = decode(item, k);
       const int h = f.h;
       const int i = f.i0 + ii;
       if (i < f.S) {
@@ -408,7 +441,7 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         for (int c = 0; c < 32; ++c) qw[c] = 0u;
       }
     };
-    if (item0 < p.n_items) fetch_q(item0);
+    if (item0 < p.n_items) fetch_q(item0, 0);
 
     int base_gb = 0, n_act = 0;
     int base_it[2] = {0, 0};
@@ -433,8 +466,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_a(set == 0 ? qu_ready : qv_ready);
     };
-    for (int item = item0; item < p.n_items; item += item_step) {
-      const Item w = decode(item);
+    for (int item = item0, ik = 0; item < p.n_items; item += item_step, ++ik) {
+      const Item w = decode(item, ik);
       const int i = w.i0 + ii;
       if (!w.active) {
         if (set == 0 && i < w.S) {
@@ -442,14 +475,14 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
 #pragma unroll
           for (int c = 0; c < 8; ++c) o[c] = make_uint4(0, 0, 0, 0);
         }
-        if (item + item_step < p.n_items) fetch_q(item + item_step);
+        if (item + item_step < p.n_items) fetch_q(item + item_step, ik + 1);
         continue;
       }
       const int len = w.len, n_kt = w.n_kt;
       // ---- operand row -> TMEM, unless the tail of the previous item already did it (see below)
       if (!pre_stored) store_q(n_act);
       pre_stored = false;
-      if (item + item_step < p.n_items) fetch_q(item + item_step);  // lands while this item's key tiles run
+      if (item + item_step < p.n_items) fetch_q(item + item_step, ik + 1);  // lands while this item's key tiles run
 
       auto fetch_window = [&](int kt) {
         const int last = base_gb + kt + 2;  // blocks complete in order
@@ -575,7 +608,7 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       asm volatile("bar.sync 1, 256;" ::: "memory");
       // The next item's operand goes into TMEM BEFORE this item's merge and write-back: its S and G MMAs then run while
       // set 0 is still busy with the context rows (qw holds the next item's row since the top of this iteration).
-      if (item + item_step < p.n_items && decode(item + item_step).active) {
+      if (item + item_step < p.n_items && decode(item + item_step, ik + 1).active) {
         store_q(n_act);
         pre_stored = true;
       }
@@ -601,7 +634,7 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           }
         }
         // the exchange rows are free again; set 1 waits for this before its next write (not after the last item)
-        if (has_next_active(item)) asm volatile("bar.arrive 2, 256;" ::: "memory");
+        if (has_next_active(item, ik)) asm volatile("bar.arrive 2, 256;" ::: "memory");
       }
     }
   }
