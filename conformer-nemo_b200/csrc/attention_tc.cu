@@ -129,9 +129,11 @@ rel_attn_tc_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_consta
   const int h = blockIdx.y;
   const int T = p.T;  // extent of the positional table (2T - 1 band rows)
   uint32_t tid;
-  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));  // volatile: keeps warp / lane in registers (no S2R re-reads)
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+  // Through a shuffle: ptxas rematerialises S2R SR_TID.X (tens of cycles) in front of the addresses that derive from the
+  // warp and lane index -- several times per key tile in the softmax warps (ncu source page); a shuffle result it keeps.
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(tid >> 5), 0);
+  const int lane = __shfl_sync(0xffffffffu, static_cast<int>(tid & 31), static_cast<int>(tid & 31));
   const bool trc = kInstr && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
   const int dbg = kInstr ? p.debug : 0;
 #define CFB_TR(slot) do { if (kInstr && trc) p.trace[slot] = clock64(); } while (0)

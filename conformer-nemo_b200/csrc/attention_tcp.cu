@@ -138,8 +138,10 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
   const int T = p.T;
   uint32_t tid;
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
+  // Through a shuffle: ptxas rematerialises S2R SR_TID.X (tens of cycles) in front of the addresses that derive from the
+  // warp and lane index -- several times per key tile in the softmax warps (ncu source page); a shuffle result it keeps.
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(tid >> 5), 0);
+  const int lane = __shfl_sync(0xffffffffu, static_cast<int>(tid & 31), static_cast<int>(tid & 31));
 
   extern __shared__ uint8_t smem_raw[];
   // Laundered through a volatile mov: ptxas otherwise REMATERIALISES the base wherever it is short of registers, and the
