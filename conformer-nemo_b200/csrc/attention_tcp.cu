@@ -365,8 +365,9 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       const uint32_t tQv = tmem_base + kColQ + 32;
       const uint32_t band_base = sbase + kOffBand;
       int base_gb = 0, n_act = 0;
-      int base_it[2] = {0, 0};
-      int prev_its[2] = {0, 0};
+      // scalars, not arrays: an index that is only known at run time puts an array in LOCAL memory, and the loads showed
+      // up as long-scoreboard stalls on the address arithmetic that follows (ncu source page)
+      int base_it0 = 0, base_it1 = 0, prev_its0 = 0, prev_its1 = 0;
       for (int item = item0, ik = 0; item < p.n_items; item += item_step, ++ik) {
         const Item w = decode(item, ik);
         if (!w.active) continue;
@@ -374,9 +375,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         if (lane == 0) ptx::mbar_arrive_a(role_sync);
         // every window of the previous item has left the ring (the sets cannot be further: their next windows need
         // the blocks issued below)
-#pragma unroll
-        for (int s = 0; s < 2; ++s)
-          if (prev_its[s] > 0) ptx::mbar_wait_a(g_free + 8 * s, (base_it[s] - 1) & 1);
+        if (prev_its0 > 0) ptx::mbar_wait_a(g_free, (base_it0 - 1) & 1);
+        if (prev_its1 > 0) ptx::mbar_wait_a(g_free + 8, (base_it1 - 1) & 1);
         for (int g = 0; g < w.n_gb; ++g) {
           const int idx = base_gb + g;
           const int bs = idx % kBandSlots;
@@ -387,7 +387,7 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           // set's) was waited for at step g-1 and tile g-6 precedes g-4 in its set: one wait per step covers all three
           if (g >= 4 && g - 4 < w.n_kt) {
             const int s = (g - 4) & 1;
-            ptx::mbar_wait_a(g_free + 8 * s, (base_it[s] + ((g - 4) >> 1)) & 1);
+            ptx::mbar_wait_a(g_free + 8 * s, ((s ? base_it1 : base_it0) + ((g - 4) >> 1)) & 1);
           }
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
@@ -399,11 +399,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
           __syncwarp();
         }
         base_gb += w.n_gb;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          prev_its[s] = w.n_kt > s ? (w.n_kt - s + 1) / 2 : 0;
-          base_it[s] += prev_its[s];
-        }
+        prev_its0 = (w.n_kt + 1) / 2, prev_its1 = w.n_kt / 2;
+        base_it0 += prev_its0, base_it1 += prev_its1;
         ++n_act;
       }
     }
@@ -446,7 +443,7 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
     if (item0 < p.n_items) fetch_q(item0, 0);
 
     int base_gb = 0, n_act = 0;
-    int base_it[2] = {0, 0};
+    int base_mine = 0, base_other = 0;  // tiles this set / the other set has processed (scalars: see the G issuer)
     bool pre_stored = false;
     // qw -> the TMEM A operand of the item that `n_started` active items precede.  Every MMA of the item before it has
     // completed when this is called (both sets passed their last o_full wait and the exchange barrier; the last window
@@ -519,7 +516,7 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
       int it = 0;
       for (int kt = set; kt < n_kt; kt += 2, ++it) {
         const int j0 = kt * kBN;
-        const int gi = base_it[set] + it;
+        const int gi = base_mine + it;
         // the shifted window row was stored a whole P V MMA ago: read it while the S MMA of this tile is still in flight
         uint32_t gw[32];
         lds_u32x32(shift_row + (sh >> 1) * 4, gw);
@@ -546,7 +543,7 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         // the exponentials of consecutive key tiles take turns on the MUFU pipe (tile kt after tile kt-1)
         // (with one tile per set the order does not matter and set 1 need not idle through set 0's write-back of the
         // previous item: 128 x 100 frames x 4 heads 30.8 -> 29.5 us; with more tiles the strict order measures better)
-        if (kt > (n_kt <= 2 ? 1 : 0)) ptx::mbar_wait_a(exp_done + 8 * (set ^ 1), (base_it[set ^ 1] + (set == 0 ? it - 1 : it)) & 1);
+        if (kt > (n_kt <= 2 ? 1 : 0)) ptx::mbar_wait_a(exp_done + 8 * (set ^ 1), (base_other + (set == 0 ? it - 1 : it)) & 1);
         float mx4[4] = {sv[0], sv[1], sv[2], sv[3]};
 #pragma unroll
         for (int c = 4; c < kBN; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], sv[c]);
@@ -591,8 +588,8 @@ rel_attn_tcp_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_const
         if (lane == 0) ptx::mbar_arrive_a(s_free + 8 * set);
       }
       base_gb += w.n_gb;
-#pragma unroll
-      for (int s = 0; s < 2; ++s) base_it[s] += n_kt > s ? (n_kt - s + 1) / 2 : 0;
+      base_mine += set == 0 ? (n_kt + 1) / 2 : n_kt / 2;
+      base_other += set == 0 ? n_kt / 2 : (n_kt + 1) / 2;
       ++n_act;
 
       // ---- merge the two sets (log-sum-exp) through the exchange buffer and write the context rows.  Set 1 goes
