@@ -121,8 +121,11 @@ __device__ __forceinline__ void epi_compute(const EpiParams& p, long long out_ro
   epi_math<EPI, kFast>(p, out_row, acc, b);
 }
 
-template <int EPI, bool kFast>
-__device__ __forceinline__ void epi_math(const EpiParams& p, long long out_row, float (&acc)[32], const float (&b)[32]) {
+// Is output row `out_row` a valid frame (false: the masked epilogues store zeros)?  A dependent global load: the
+// tensor-core kernels ask once per tile BEFORE they wait for the accumulator (epi_math_keep), not in front of the
+// first arithmetic of the tile.
+template <int EPI>
+__device__ __forceinline__ bool epi_keep(const EpiParams& p, long long out_row) {
   bool keep = true;
   if constexpr (EPI == EPI_LINEAR || EPI == EPI_SWISH || EPI == EPI_RELU || EPI == EPI_GLU) {
     if (p.row_t != nullptr) {
@@ -133,6 +136,19 @@ __device__ __forceinline__ void epi_math(const EpiParams& p, long long out_row, 
       keep = t < p.lens[seq];
     }
   }
+  return keep;
+}
+
+template <int EPI, bool kFast>
+__device__ __forceinline__ void epi_math_keep(const EpiParams& p, bool keep, float (&acc)[32], const float (&b)[32]);
+
+template <int EPI, bool kFast>
+__device__ __forceinline__ void epi_math(const EpiParams& p, long long out_row, float (&acc)[32], const float (&b)[32]) {
+  epi_math_keep<EPI, kFast>(p, epi_keep<EPI>(p, out_row), acc, b);
+}
+
+template <int EPI, bool kFast>
+__device__ __forceinline__ void epi_math_keep(const EpiParams& p, bool keep, float (&acc)[32], const float (&b)[32]) {
   if constexpr (EPI == EPI_LINEAR || EPI == EPI_SWISH || EPI == EPI_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {

@@ -159,6 +159,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int half = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     uint8_t* stage_base = smem + kStagingOffset + (warp - 2) * 8192;
+    // 32-bit shared-window addresses for the staging rows and the bias: through the rounded-up generic pointer the compiler
+    // cannot prove the address space and emits generic LD.E / ST.E (long-scoreboard) for every access of the epilogue
+    const uint32_t stage_a = ptx::smem_u32(stage_base), bias_a0 = ptx::smem_u32(smem + kBiasOffset);
     const uint32_t swz = static_cast<uint32_t>(lane & 7);
     uint32_t box_counter = 0;
     int it = 0;
@@ -168,15 +171,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m_blk = 2 * (tile / p.num_n_tiles) + static_cast<int>(rank);  // this CTA's 128-row block
       const long long out_row = static_cast<long long>(m_blk) * kBlockM + row_in_tile;
       const bool row_ok = out_row < p.ep.M;
-      float* bias_s = reinterpret_cast<float*>(smem + kBiasOffset) + buf * kBN;
+      const uint32_t bias_a = bias_a0 + buf * kBN * 4;
       {
         const int e = static_cast<int>(threadIdx.x) - 64;
         if (e < kBN) {
           const int col = n_blk * kBN + e;
-          bias_s[e] = (p.ep.bias != nullptr && col < p.ep.N) ? __ldg(p.ep.bias + col) : 0.f;
+          ptx::sts_f32(bias_a + 4 * e, (p.ep.bias != nullptr && col < p.ep.N) ? __ldg(p.ep.bias + col) : 0.f);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
+      const bool keep = row_ok ? epi_keep<EPI>(p.ep, out_row) : true;  // its load is in flight during the accumulator wait
       const bool trc = p.trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 16;
       if (trc) p.trace[it * 4 + 0] = clock64();
       ptx::mbar_wait_a(acc_full + 8 * buf, (it >> 1) & 1);
@@ -193,7 +197,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint8_t* sbuf = stage_base + (box_counter & 1u) * 4096;
           if (lane == 0) ptx::bulk_wait_read<1>();
           __syncwarp();
-          uint8_t* srow = sbuf + lane * 128;
+          const uint32_t srow = stage_a + static_cast<uint32_t>(sbuf - stage_base) + lane * 128;
 #pragma unroll
           for (int ch = 0; ch < kChunks; ++ch) {
             uint32_t v[32];
@@ -207,20 +211,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 epi_compute<EPI, kFast>(p.ep, out_row, acc_col0 + ch * 32, acc, pass);
               } else {
                 float b[32];
-                const float4* bs = reinterpret_cast<const float4*>(bias_s + box * kAccPerBox + ch * 32);
+                const uint32_t bs = bias_a + 4 * (box * kAccPerBox + ch * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float4 t = bs[j];
+                  const float4 t = ptx::lds_f32x4(bs + 16 * j);
                   b[4 * j] = t.x, b[4 * j + 1] = t.y, b[4 * j + 2] = t.z, b[4 * j + 3] = t.w;
                 }
-                epi_math<EPI, kFast>(p.ep, out_row, acc, b);
+                epi_math_keep<EPI, kFast>(p.ep, keep, acc, b);
               }
             }
             if constexpr (sizeof(TOut) == 4) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(srow + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
-                    make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                ptx::sts128(srow + ((static_cast<uint32_t>(j) ^ swz) << 4), __float_as_uint(acc[4 * j]), __float_as_uint(acc[4 * j + 1]),
+                            __float_as_uint(acc[4 * j + 2]), __float_as_uint(acc[4 * j + 3]));
             } else {
               constexpr int kPieces = (EPI == EPI_GLU) ? 2 : 4;
 #pragma unroll
@@ -230,7 +234,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 u.y = ptx::pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
                 u.z = ptx::pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]);
                 u.w = ptx::pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
-                *reinterpret_cast<uint4*>(srow + ((static_cast<uint32_t>(ch * kPieces + j) ^ swz) << 4)) = u;
+                ptx::sts128(srow + ((static_cast<uint32_t>(ch * kPieces + j) ^ swz) << 4), u.x, u.y, u.z, u.w);
               }
             }
           }
