@@ -294,7 +294,7 @@ dw_pw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
       uint8_t* stage_base = smem + pw * 8192;
       const uint32_t swz = static_cast<uint32_t>(lane & 7);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-      const float* bias_s = reinterpret_cast<const float*>(smem + kOffBias);
+      const uint32_t stage_a = ptx::smem_u32(stage_base), bias_a = ptx::smem_u32(smem + kOffBias);
       uint32_t cnt = 0;
       const int boxes = p.d / 32;
 #pragma unroll 1
@@ -305,14 +305,15 @@ dw_pw_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
         if (lane == 0) ptx::bulk_wait_read<1>();  // the reduce that last read this staging box has drained it
         __syncwarp();
         ptx::tc_wait_ld();
-        uint8_t* srow = sbuf + lane * 128;
-        const float4* bs = reinterpret_cast<const float4*>(bias_s + box * 32);
+        // shared-space accesses by 32-bit address (through the rounded-up generic pointer these were LD.E / ST.E)
+        const uint32_t srow = stage_a + (cnt & 1u) * 4096 + lane * 128;
+        const uint32_t bs = bias_a + 4 * box * 32;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 bb = bs[j];
-          *reinterpret_cast<float4*>(srow + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
-              make_float4(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y,
-                          __uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w);
+          const float4 bb = ptx::lds_f32x4(bs + 16 * j);
+          ptx::sts128(srow + ((static_cast<uint32_t>(j) ^ swz) << 4), __float_as_uint(__uint_as_float(v[4 * j]) + bb.x),
+                      __float_as_uint(__uint_as_float(v[4 * j + 1]) + bb.y), __float_as_uint(__uint_as_float(v[4 * j + 2]) + bb.z),
+                      __float_as_uint(__uint_as_float(v[4 * j + 3]) + bb.w));
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();
