@@ -40,6 +40,45 @@ def test_library_exports_every_declared_symbol(lib):
     assert "libcuda.so" not in ldd and "libtorch" not in ldd
 
 
+def test_integration_notes_name_every_entry_point():
+    """INTEGRATION.md is the maintainer-facing map of the C ABI: every exported entry point is named there."""
+    header = open(os.path.join(ROOT, "include", "cfb.h")).read()
+    declared = set(re.findall(r"CFB_API\s+[\w\s\*]+?\b(cfb_\w+)\s*\(", header))
+    notes = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = sorted(n for n in declared if n not in notes)
+    assert not missing, missing
+
+
+def test_hot_kernels_keep_index_registers_out_of_the_tile_loops(lib):
+    """ptxas rematerialises special-register reads (S2R SR_TID.X, SR_CgaCtaId: tens of cycles each) wherever it is short of
+    registers; in the attention kernels that was several reads per key tile.  The fixes route the
+    values through a shuffle / a volatile mov; this pins the count so that a refactor does not silently bring them back."""
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip("cuobjdump unavailable")
+    counts, fn = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+        elif fn and ("SR_TID" in line or "SR_CgaCtaId" in line):
+            counts[fn] = counts.get(fn, 0) + 1
+    attn = {k: v for k, v in counts.items() if "rel_attn_tc" in k}
+    assert attn, "attention kernels not found in the library"
+    for name, n in attn.items():
+        assert n <= 6, (name, n)  # set-up and tear-down reads only (was 25 + 14 in the persistent kernel)
+    # and no local-memory frames in the tensor-core kernels (run-time indexed counters were LDL in front of mbarrier waits)
+    res = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    fn = None
+    for line in res.splitlines():
+        m = re.search(r"Function (\S+?):", line)
+        if m:
+            fn = m.group(1)
+        m = re.search(r"STACK:(\d+)", line)
+        if m and fn and any(k in fn for k in ("rel_attn_tc", "gemm_tc", "dw_pw_kernel")):
+            assert int(m.group(1)) == 0, (fn, line.strip())
+
+
 def test_sass_contains_blackwell_tensor_core_and_tma_instructions(lib):
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     if not sass:
